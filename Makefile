@@ -1,0 +1,27 @@
+# Builds libonmf_b200.so (sm_100a only) in-tree, and the oracle's C restatement.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -std=c++17 -O3 -lineinfo $(ARCH) -Xcompiler -fPIC -Xptxas -v
+CSRC      := onmf_ontf_ndl_b200/csrc
+SRCS      := $(wildcard $(CSRC)/*.cu)
+OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
+LIB       := onmf_ontf_ndl_b200/libonmf_b200.so
+
+all: $(LIB) oracle
+
+build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/onmf_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+
+oracle: oracle/liblars_oracle.so
+
+oracle/liblars_oracle.so: oracle/lars_oracle.c
+	gcc -O2 -fPIC -shared -o $@ $< -lm
+
+clean:
+	rm -rf build $(LIB) oracle/liblars_oracle.so
+
+.PHONY: all oracle clean

@@ -1,0 +1,147 @@
+/*
+ * onmf_b200.h -- C ABI of libonmf_b200.so: hand-written sm_100a CUDA kernels for the online
+ * NMF/NTF dictionary-learning hot path of HanbaekLyu/ONMF_ONTF_NDL.
+ *
+ * The reference has no FFI layer (it is pure Python: numpy + scikit-learn); the boundary a
+ * maintainer would bind is its Python class API (src/onmf.py, src/ontf.py).  Each entry point
+ * below replaces one numpy/sklearn call inside those classes and cites it.  INTEGRATION.md shows
+ * the ctypes stub that goes into the reference's `Online_NTF` / `Online_NMF` methods.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named `host_*`; the caller owns all buffers;
+ *     nothing is allocated inside the library; `stream` is a cudaStream_t passed as void*.
+ *   - dtype: ONMF_F32 (production) or ONMF_F64 (parity mode; the reference computes in float64).
+ *   - "sample-major" layout: a minibatch is stored one sample per row,
+ *         Xt (n x d), Ct = Xt W (n x k), Ht (n x k)       all row-major, leading dim = row length.
+ *     (the reference's `joint_sparse_code_tensor` already returns H as n x r, src/ontf.py:86.)
+ *     W is (d x k) row-major, A is (k x k), B is (k x d) row-major -- the reference's shapes.
+ *   - every function returns 0 on success, a negative ONMF_E_* code otherwise;
+ *     onmf_last_error() returns a thread-local message.
+ *   - no function synchronises the stream; none is a CPU fallback.
+ */
+#ifndef ONMF_B200_H
+#define ONMF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ONMF_F32 0
+#define ONMF_F64 1
+
+#define ONMF_OK 0
+#define ONMF_E_ARG (-1)        /* bad argument (null pointer, unsupported size)            */
+#define ONMF_E_CUDA (-2)       /* a CUDA runtime call failed; see onmf_last_error()       */
+#define ONMF_E_UNSUPPORTED (-3)/* shape outside what the kernels were instantiated for    */
+#define ONMF_E_WORKSPACE (-4)  /* workspace too small                                     */
+
+/* library / build identification */
+int onmf_version(void);                      /* 100*major + minor                                   */
+const char* onmf_last_error(void);
+int onmf_built_arch(void);                   /* 100 => sm_100a                                      */
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  patch gather / matricization
+ * replaces: the np.append patch loops image_reconstruction.py:184-205,
+ *           image_reconstruction_tensor.py:102-123, ising_reconstruction.py:56-65 and
+ *           tl_unfold(...)[.T] + X_unfold[:, idx]  (src/ontf.py:203-208, :229-231)
+ * ------------------------------------------------------------------------------------------- */
+
+/* img: (H x Wd x C) row-major (C=1 gray / Ising lattice, C=3 colour); coords: n pairs (row, col) of
+ * int32 top-left corners; out Xt (n x ld), Xt[j, (r*p + c)*C + ch] = img[a_j + r, b_j + c, ch]
+ * -- the HWC feature order of the reference's reshape(k**2, 3) + mode-2 joint unfolding. */
+int onmf_gather_patches(int dtype, const void* img, int H, int Wd, int C, const int32_t* coords,
+                        int64_t n, int p, void* Xt, int64_t ld, void* stream);
+
+/* column gather of a resident sample-major data pool: out[j, :] = pool[idx[j], :]
+ * (X_batch = X_unfold[:, idx], src/ontf.py:231; idx as int64 like numpy's randint). */
+int onmf_gather_rows(int dtype, const void* pool, int64_t n_pool, int d, const int64_t* idx,
+                     int64_t n, void* Xt, void* stream);
+
+/* transpose/convert a (d x n) row-major matrix (the reference's X layout, any of f32/f64) into the
+ * sample-major (n x d) layout in `dtype_out`.  Also used for H (k x n) <-> Ht. */
+int onmf_transpose(int dtype_in, int dtype_out, const void* src, int64_t rows, int64_t cols,
+                   void* dst, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  Gram and covariance products
+ * replaces: gram = D D^T, cov = D X^T  (sklearn/decomposition/_dict_learning.py:422,426, reached
+ *           from src/ontf.py:86) and A = W.T @ W, B = W.T @ X (src/onmf.py:242-243)
+ * ------------------------------------------------------------------------------------------- */
+int onmf_gram(int dtype, const void* W, int d, int k, void* G /* k x k */, void* stream);
+int onmf_cov(int dtype, const void* Xt, int64_t n, int d, const void* W, int k,
+             void* Ct /* n x k */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  batched positive LARS-lasso (the sparse coder)
+ * replaces: SparseCoder(..., 'lasso_lars', positive_code=True).transform (src/ontf.py:79-86), i.e.
+ *           LassoLars.fit's per-sample loop sklearn/linear_model/_least_angle.py:1136-1153 over
+ *           _lars_path_solver (:415-917, Gram mode, method='lasso', positive, return_path=False).
+ * Per column: argmin_{h>=0} 0.5||x - W h||^2 + alpha*sum(h), following the same homotopy path and
+ * the same stopping / last-segment interpolation rule (alpha_min = alpha/d, float32-eps equality
+ * tolerance), so results agree with the reference also where sklearn is not at the exact optimum.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  unsigned long long columns;      /* columns solved                                   */
+  unsigned long long knots;        /* LARS iterations executed (sum over columns)      */
+  unsigned long long sum_active;   /* sum over knots of the active-set size s          */
+  unsigned long long sum_active2;  /* sum over knots of s^2                            */
+  unsigned long long drops;        /* lasso drop events                                */
+  unsigned long long overflow;     /* columns re-solved by the large-active-set path   */
+  unsigned long long flagged;      /* columns that hit degenerate / ill-conditioned / max_iter exits */
+  unsigned long long max_active;   /* largest active set seen                          */
+} onmf_lars_stats;
+
+/* bytes of workspace onmf_lasso_lars needs for (dtype, k, n) */
+size_t onmf_lasso_lars_workspace(int dtype, int k, int64_t n);
+
+/* G (k x k), Ct (n x k) -> Ht (n x k).  d = number of features (enters only sklearn's alpha/d scaling
+ * of the stopping rule).  stats may be NULL (device pointer to onmf_lars_stats, accumulated into). */
+int onmf_lasso_lars(int dtype, const void* G, const void* Ct, int64_t n, int k, int d, double alpha,
+                    int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
+                    onmf_lars_stats* stats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  surrogate aggregation
+ * replaces: A1 = (1-w) A + w H^T H ; B1 = (1-w) B + w H^T X^T   (src/ontf.py:147-148,
+ *           src/onmf.py:155-156), optional C1 = (1-w) C + w X X^T (src/onmf.py:157-158)
+ * Two phases so that a multi-GPU run can all-reduce the packed partial sums in between:
+ *   partial:  P = [ Ht^T Ht | Ht^T Xt ]   packed (k x (k+d)) row-major, THIS rank's columns only
+ *   blend:    A = (1-w) A + w P[:, :k] ;  B = (1-w) B + w P[:, k:]
+ * ------------------------------------------------------------------------------------------- */
+size_t onmf_surrogate_workspace(int dtype, int64_t n, int k, int d);
+int onmf_surrogate_partial(int dtype, const void* Ht, const void* Xt, int64_t n, int k, int d,
+                           void* P /* k x (k+d) */, void* workspace, size_t workspace_bytes,
+                           void* stream);
+int onmf_surrogate_blend(int dtype, const void* P, int k, int d, double w, void* A, void* B,
+                         void* stream);
+/* optional d x d aggregate: Cagg = (1-w) Cagg + w Xt^T Xt   (single rank; P2 is a d x d scratch) */
+int onmf_xxt_partial(int dtype, const void* Xt, int64_t n, int d, void* P2, void* workspace,
+                     size_t workspace_bytes, void* stream);
+int onmf_axpby(int dtype, int64_t count, double a, const void* x, double b, void* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  dictionary update (one block-coordinate-descent sweep)
+ * replaces: update_dict  src/ontf.py:91-115 == src/onmf.py:92-116
+ *   for j in 0..k-1:  W[:,j] -= (W A[:,j] - B[j,:]^T) / (A[j,j] + 1);  W[:,j] = max(W[:,j], 0);
+ *                     W[:,j] /= max(1, ||W[:,j]||_2)
+ * W_in and W_out (d x k) may alias.
+ * ------------------------------------------------------------------------------------------- */
+int onmf_update_dict(int dtype, const void* W_in, const void* A, const void* B, int d, int k,
+                     void* W_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * secondary coder: row-wise projected gradient (shipped src/onmf.py:233-271 with r=None),
+ * ONE outer iteration `it` (step 1/(sqrt(it+10) (G_qq+1))), in place on Ht (n x k).
+ * The outer loop / stopping test stays on the host (it needs spectral norms).
+ * ------------------------------------------------------------------------------------------- */
+int onmf_pgd_sweep(int dtype, const void* G, const void* Ct, int64_t n, int k, double alpha,
+                   int it, void* Ht, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ONMF_B200_H */

@@ -1,0 +1,204 @@
+"""ctypes binding of libonmf_b200.so (the C ABI declared in include/onmf_b200.h).
+
+There is no CPU fallback: importing the kernels without the built library raises, and every
+wrapper raises `OnmfKernelError` on a non-zero status.  PyTorch is used only as the owner of
+device memory and streams (tensors are passed as raw `data_ptr()`s).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+F32, F64 = 0, 1
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libonmf_b200.so")
+
+
+class OnmfKernelError(RuntimeError):
+    pass
+
+
+class LarsStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_ulonglong) for n in
+                ("columns", "knots", "sum_active", "sum_active2", "drops", "overflow", "flagged",
+                 "max_active")]
+
+
+STATS_FIELDS = [f[0] for f in LarsStats._fields_]
+
+_vp, _i, _i64, _dbl, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/onmf_b200.h declares
+SIGNATURES = {
+    "onmf_version": (_i, []),
+    "onmf_last_error": (ctypes.c_char_p, []),
+    "onmf_built_arch": (_i, []),
+    "onmf_gather_patches": (_i, [_i, _vp, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp]),
+    "onmf_gather_rows": (_i, [_i, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
+    "onmf_transpose": (_i, [_i, _i, _vp, _i64, _i64, _vp, _vp]),
+    "onmf_gram": (_i, [_i, _vp, _i, _i, _vp, _vp]),
+    "onmf_cov": (_i, [_i, _vp, _i64, _i, _vp, _i, _vp, _vp]),
+    "onmf_lasso_lars_workspace": (_sz, [_i, _i, _i64]),
+    "onmf_lasso_lars": (_i, [_i, _vp, _vp, _i64, _i, _i, _dbl, _i, _vp, _vp, _sz, _vp, _vp]),
+    "onmf_surrogate_workspace": (_sz, [_i, _i64, _i, _i]),
+    "onmf_surrogate_partial": (_i, [_i, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _vp]),
+    "onmf_surrogate_blend": (_i, [_i, _vp, _i, _i, _dbl, _vp, _vp, _vp]),
+    "onmf_xxt_partial": (_i, [_i, _vp, _i64, _i, _vp, _vp, _sz, _vp]),
+    "onmf_axpby": (_i, [_i, _i64, _dbl, _vp, _dbl, _vp, _vp]),
+    "onmf_update_dict": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "onmf_pgd_sweep": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libonmf_b200.so (built in-tree by `make` / `__graft_entry__.build()`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise OnmfKernelError(
+            "libonmf_b200.so is not built (%s). Run `make` or `python -c 'import __graft_entry__ as g; "
+            "g.build()'` at the repo root; there is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load().onmf_last_error().decode(errors="replace")
+        raise OnmfKernelError("%s failed (status %d): %s" % (what, rc, msg))
+
+
+def dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise OnmfKernelError("unsupported dtype %s (float32 / float64 only)" % t.dtype)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _req(t, name, dtype=None):
+    if not t.is_cuda:
+        raise OnmfKernelError("%s must be a CUDA tensor (no CPU path)" % name)
+    if not t.is_contiguous():
+        raise OnmfKernelError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise OnmfKernelError("%s must have dtype %s" % (name, dtype))
+
+
+# ---- thin wrappers (shapes documented in include/onmf_b200.h) --------------------------------
+
+def gather_patches(img, coords, p, out, stream=None):
+    _req(img, "img"); _req(coords, "coords", torch.int32); _req(out, "out", img.dtype)
+    H, Wd = img.shape[0], img.shape[1]
+    C = img.shape[2] if img.dim() == 3 else 1
+    n = coords.shape[0]
+    _check(load().onmf_gather_patches(dt(img), _ptr(img), H, Wd, C, _ptr(coords), n, p, _ptr(out),
+                                      out.stride(0) if n else p * p * C, _stream(stream)), "onmf_gather_patches")
+    return out
+
+
+def gather_rows(pool, idx, out, stream=None):
+    _req(pool, "pool"); _req(idx, "idx", torch.int64); _req(out, "out", pool.dtype)
+    _check(load().onmf_gather_rows(dt(pool), _ptr(pool), pool.shape[0], pool.shape[1], _ptr(idx), idx.shape[0],
+                                   _ptr(out), _stream(stream)), "onmf_gather_rows")
+    return out
+
+
+def transpose(src, out, stream=None):
+    _req(src, "src"); _req(out, "out")
+    rows, cols = src.shape
+    _check(load().onmf_transpose(dt(src), dt(out), _ptr(src), rows, cols, _ptr(out), _stream(stream)), "onmf_transpose")
+    return out
+
+
+def gram(W, G, stream=None):
+    _req(W, "W"); _req(G, "G", W.dtype)
+    d, k = W.shape
+    _check(load().onmf_gram(dt(W), _ptr(W), d, k, _ptr(G), _stream(stream)), "onmf_gram")
+    return G
+
+
+def cov(Xt, W, Ct, stream=None):
+    _req(Xt, "Xt"); _req(W, "W", Xt.dtype); _req(Ct, "Ct", Xt.dtype)
+    n, d = Xt.shape
+    _check(load().onmf_cov(dt(Xt), _ptr(Xt), n, d, _ptr(W), W.shape[1], _ptr(Ct), _stream(stream)), "onmf_cov")
+    return Ct
+
+
+def lasso_lars_workspace(dtype, k, n):
+    return int(load().onmf_lasso_lars_workspace(F64 if dtype == torch.float64 else F32, k, n))
+
+
+def lasso_lars(G, Ct, d, alpha, Ht, workspace, max_iter=1000, stats=None, stream=None):
+    _req(G, "G"); _req(Ct, "Ct", G.dtype); _req(Ht, "Ht", G.dtype); _req(workspace, "workspace", torch.uint8)
+    n, k = Ct.shape
+    _check(load().onmf_lasso_lars(dt(G), _ptr(G), _ptr(Ct), n, k, d, float(alpha), int(max_iter), _ptr(Ht),
+                                  _ptr(workspace), workspace.numel(), _ptr(stats), _stream(stream)), "onmf_lasso_lars")
+    return Ht
+
+
+def surrogate_workspace(dtype, n, k, d):
+    return int(load().onmf_surrogate_workspace(F64 if dtype == torch.float64 else F32, n, k, d))
+
+
+def surrogate_partial(Ht, Xt, P, workspace, stream=None):
+    _req(Ht, "Ht"); _req(Xt, "Xt", Ht.dtype); _req(P, "P", Ht.dtype); _req(workspace, "workspace", torch.uint8)
+    n, k = Ht.shape
+    d = Xt.shape[1]
+    _check(load().onmf_surrogate_partial(dt(Ht), _ptr(Ht), _ptr(Xt), n, k, d, _ptr(P), _ptr(workspace),
+                                         workspace.numel(), _stream(stream)), "onmf_surrogate_partial")
+    return P
+
+
+def surrogate_blend(P, w, A, B, stream=None):
+    _req(P, "P"); _req(A, "A", P.dtype); _req(B, "B", P.dtype)
+    k, d = B.shape
+    _check(load().onmf_surrogate_blend(dt(P), _ptr(P), k, d, float(w), _ptr(A), _ptr(B), _stream(stream)),
+           "onmf_surrogate_blend")
+
+
+def xxt_partial(Xt, P2, workspace, stream=None):
+    _req(Xt, "Xt"); _req(P2, "P2", Xt.dtype)
+    n, d = Xt.shape
+    _check(load().onmf_xxt_partial(dt(Xt), _ptr(Xt), n, d, _ptr(P2), _ptr(workspace),
+                                   workspace.numel() if workspace is not None else 0, _stream(stream)), "onmf_xxt_partial")
+    return P2
+
+
+def axpby(a, x, b, y, stream=None):
+    _req(x, "x"); _req(y, "y", x.dtype)
+    _check(load().onmf_axpby(dt(x), x.numel(), float(a), _ptr(x), float(b), _ptr(y), _stream(stream)), "onmf_axpby")
+
+
+def update_dict(W, A, B, W_out, stream=None):
+    _req(W, "W"); _req(A, "A", W.dtype); _req(B, "B", W.dtype); _req(W_out, "W_out", W.dtype)
+    d, k = W.shape
+    _check(load().onmf_update_dict(dt(W), _ptr(W), _ptr(A), _ptr(B), d, k, _ptr(W_out), _stream(stream)), "onmf_update_dict")
+    return W_out
+
+
+def pgd_sweep(G, Ct, alpha, it, Ht, stream=None):
+    _req(G, "G"); _req(Ct, "Ct", G.dtype); _req(Ht, "Ht", G.dtype)
+    n, k = Ct.shape
+    _check(load().onmf_pgd_sweep(dt(G), _ptr(G), _ptr(Ct), n, k, float(alpha), int(it), _ptr(Ht), _stream(stream)),
+           "onmf_pgd_sweep")
+    return Ht

@@ -1,0 +1,163 @@
+// K5 -- dictionary update: one Gauss-Seidel block-coordinate sweep over the k atoms.
+//
+// Replaces update_dict (reference src/ontf.py:91-115 == src/onmf.py:92-116):
+//   for j in 0..k-1:  W[:,j] -= (1/(A[j,j]+1)) * (W A[:,j] - B[j,:]);  W[:,j] = max(W[:,j], 0);
+//                     W[:,j] *= 1 / max(1, ||W[:,j]||_2)
+//
+// The sweep is sequential in j but separable over the d rows of W except for the column norm.  ONE
+// thread-block cluster owns the whole dictionary: CTA r keeps a row slab of W resident in shared memory
+// (global W is read once and written once per sweep), TPR lanes cooperate on one row's dot product with
+// the current column of A, and the k column norms are cluster-wide reductions through distributed
+// shared memory (every CTA pushes its partial sum of squares into every peer's slot, one
+// barrier.cluster per atom, partials summed in rank order so all CTAs -- and all GPUs of a
+// data-parallel run -- get bit-identical dictionaries).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace onmf {
+
+constexpr int BCD_MAX_CLUSTER = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win, const T* __restrict__ A, const T* __restrict__ B,
+                           T* __restrict__ Wout, int d, int k, int rpc, int ks, int tpr) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Ws = reinterpret_cast<T*>(smem_raw);                  // rpc x ks slab
+  T* aj = Ws + (size_t)rpc * ks;                           // 2 x k   (double-buffered column of A)
+  T* warp_part = aj + 2 * k;                               // 32
+  T* slots = warp_part + 32;                               // 2 x BCD_MAX_CLUSTER (written by peers)
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int row0 = rank * rpc;
+  const int nrows = max(0, min(rpc, d - row0));
+
+  // slab load (coalesced along k)
+  for (int idx = tid; idx < rpc * k; idx += nthr) {
+    int r = idx / k, q = idx - r * k;
+    Ws[(size_t)r * ks + q] = (r < nrows) ? Win[(size_t)(row0 + r) * k + q] : T(0);
+  }
+  for (int q = tid; q < k; q += nthr) aj[q] = A[(size_t)q * k + 0];
+  if (tid < 2 * BCD_MAX_CLUSTER) slots[tid] = T(0);
+  cluster.sync();
+
+  const int rl = tid / tpr;          // local row handled by this lane team
+  const int tl = tid % tpr;          // lane inside the team
+  const bool has_row = rl < nrows;
+  const T* wrow = Ws + (size_t)rl * ks;
+
+  for (int j = 0; j < k; ++j) {
+    const int par = j & 1;
+    const T* a = aj + par * k;
+    // prefetch next column of A into registers (strided global read, L2 resident)
+    T nxt[4];
+    int nq = 0;
+    if (j + 1 < k)
+      for (int q = tid; q < k && nq < 4; q += nthr) nxt[nq++] = A[(size_t)q * k + (j + 1)];
+    T acc0 = T(0), acc1 = T(0);
+    if (has_row) {
+      int q = tl;
+      for (; q + tpr < k; q += 2 * tpr) {
+        acc0 += wrow[q] * a[q];
+        acc1 += wrow[q + tpr] * a[q + tpr];
+      }
+      if (q < k) acc0 += wrow[q] * a[q];
+    }
+    T dot = acc0 + acc1;
+    for (int off = tpr >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    T wnew = T(0);
+    if (has_row) {
+      const T c = T(1) / (a[j] + T(1));
+      wnew = wrow[j] - c * (dot - B[(size_t)j * d + row0 + rl]);
+      wnew = wnew > T(0) ? wnew : T(0);
+    }
+    T sq = (has_row && tl == 0) ? wnew * wnew : T(0);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if ((tid & 31) == 0) warp_part[tid >> 5] = sq;
+    __syncthreads();
+    if (tid < 32) {
+      T v = (tid < (nthr + 31) / 32) ? warp_part[tid] : T(0);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (tid < csize) {
+        T* peer = cluster.map_shared_rank(slots, tid);
+        peer[par * BCD_MAX_CLUSTER + rank] = v;
+      }
+    }
+    // store the prefetched column for the next atom (other parity buffer: nobody reads it now)
+    if (j + 1 < k) {
+      int i = 0;
+      for (int q = tid; q < k && i < 4; q += nthr) aj[(par ^ 1) * k + q] = nxt[i++];
+      for (int q = tid + 4 * nthr; q < k; q += nthr) aj[(par ^ 1) * k + q] = A[(size_t)q * k + (j + 1)];
+    }
+    cluster.sync();
+    T tot = T(0);
+    for (int r = 0; r < csize; ++r) tot += slots[par * BCD_MAX_CLUSTER + r];
+    const T nrm = sqrt(tot);
+    const T sc = T(1) / (nrm > T(1) ? nrm : T(1));
+    if (has_row && tl == 0) Ws[(size_t)rl * ks + j] = sc * wnew;
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nrows * k; idx += nthr) {
+    int r = idx / k, q = idx - r * k;
+    Wout[(size_t)(row0 + r) * k + q] = Ws[(size_t)r * ks + q];
+  }
+}
+
+template <typename T>
+static int update_dict_t(const T* Win, const T* A, const T* B, int d, int k, T* Wout, cudaStream_t st) {
+  const size_t smem_cap = (size_t)max_smem_optin() - 1024;
+  // smallest power-of-two cluster whose slabs fit; prefer <= 128 rows per CTA so several lanes share a row
+  int cs = 1;
+  int rpc = 0, tpr = 1, ks = 0;
+  size_t smem = 0;
+  for (;; cs *= 2) {
+    if (cs > BCD_MAX_CLUSTER) return fail(ONMF_E_UNSUPPORTED, "update_dict: d*k too large for one 16-CTA cluster");
+    rpc = cdiv(d, cs);
+    tpr = 32;
+    while (tpr > 1 && rpc * tpr > 1024) tpr >>= 1;
+    while (tpr > 1 && tpr * 2 > k) tpr >>= 1;
+    ks = round_up(k, 32) + (tpr < 32 ? tpr : 1);
+    smem = ((size_t)rpc * ks + 2 * (size_t)k + 32 + 2 * BCD_MAX_CLUSTER) * sizeof(T);
+    bool fits = smem <= smem_cap && rpc <= 1024;
+    if (fits && (rpc <= 128 || cs >= 8)) break;
+    if (fits && cs * 2 > BCD_MAX_CLUSTER) break;
+  }
+  int threads = round_up(rpc * tpr, 32);
+  if (threads > 1024) threads = 1024;
+  auto kern = bcd_kernel<T>;
+  ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (cs > 8) ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ONMF_CUDA(cudaLaunchKernelEx(&cfg, kern, Win, A, B, Wout, d, k, rpc, ks, tpr));
+  return ONMF_OK;
+}
+
+}  // namespace onmf
+
+extern "C" int onmf_update_dict(int dtype, const void* W_in, const void* A, const void* B, int d, int k, void* W_out,
+                                void* stream) {
+  using namespace onmf;
+  if (!W_in || !A || !B || !W_out || d <= 0 || k <= 0) return fail(ONMF_E_ARG, "update_dict: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == ONMF_F32) return update_dict_t<float>((const float*)W_in, (const float*)A, (const float*)B, d, k, (float*)W_out, st);
+  if (dtype == ONMF_F64) return update_dict_t<double>((const double*)W_in, (const double*)A, (const double*)B, d, k, (double*)W_out, st);
+  return fail(ONMF_E_ARG, "update_dict: bad dtype");
+}

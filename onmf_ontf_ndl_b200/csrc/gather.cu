@@ -1,0 +1,199 @@
+// K1 -- patch gather, minibatch row gather, layout/precision conversion; plus the secondary
+// projected-gradient coder sweep.
+//
+// Replaces the drivers' O(N^2) np.append patch loops (reference image_reconstruction.py:184-205,
+// image_reconstruction_tensor.py:102-123, ising_reconstruction.py:56-65), the matricization
+// tl_unfold(...)[.T] (src/ontf.py:203-208) and the minibatch slice X_unfold[:, idx] (src/ontf.py:231).
+// All three are pure data movement: one coalesced read and one coalesced write per element, output in
+// the sample-major layout (one sample per row) every other kernel consumes.
+#include "common.cuh"
+
+namespace onmf {
+
+template <typename T>
+__global__ void gather_patches_kernel(const T* __restrict__ img, int H, int Wd, int C, const int32_t* __restrict__ coords,
+                                      long long n, int p, T* __restrict__ Xt, long long ld) {
+  // one warp per (patch, patch-row): the p*C values of a patch row are contiguous in the image and in Xt
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int run = p * C;
+  for (long long t = wid; t < n * p; t += nw) {
+    const long long j = t / p;
+    const int r = (int)(t - j * p);
+    const int a = coords[2 * j], b = coords[2 * j + 1];
+    const T* src = img + ((size_t)(a + r) * Wd + b) * C;
+    T* dst = Xt + (size_t)j * ld + (size_t)r * run;
+    for (int e = lane; e < run; e += 32) dst[e] = src[e];
+  }
+}
+
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ pool, int d, const long long* __restrict__ idx, long long n,
+                                   T* __restrict__ Xt) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long j = wid; j < n; j += nw) {
+    const T* src = pool + (size_t)idx[j] * d;
+    T* dst = Xt + (size_t)j * d;
+    for (int e = lane; e < d; e += 32) dst[e] = src[e];
+  }
+}
+
+// dst (cols x rows) = src (rows x cols)^T with conversion; 32 x 32 tiles through shared memory
+template <typename TI, typename TO>
+__global__ void transpose_kernel(const TI* __restrict__ src, long long rows, long long cols, TO* __restrict__ dst) {
+  __shared__ TO tile[32][33];
+  const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    long long r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = (TO)src[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    long long c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+// one outer iteration of the shipped projected-gradient coder (reference src/onmf.py:252-263, r=None):
+// for q in 0..k-1:  h_q <- max(h_q - (G[q,:] h - c_q + alpha) / (sqrt(it+10) (G_qq+1)), 0), Gauss-Seidel in q,
+// independently per sample.  One warp per sample; h lives in registers (atom i on lane i%32).
+template <typename T, int NA>
+__global__ void pgd_sweep_kernel(const T* __restrict__ G, const T* __restrict__ Ct, long long n, int k, T alpha, T scale,
+                                 T* __restrict__ Ht) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Gs = reinterpret_cast<T*>(smem_raw);
+  for (int i = threadIdx.x; i < k * k; i += blockDim.x) Gs[i] = G[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long j = wid; j < n; j += nw) {
+    T h[NA];
+#pragma unroll
+    for (int m = 0; m < NA; ++m) {
+      int i = lane + 32 * m;
+      h[m] = i < k ? Ht[(size_t)j * k + i] : T(0);
+    }
+    for (int q = 0; q < k; ++q) {
+      T part = T(0);
+#pragma unroll
+      for (int m = 0; m < NA; ++m) {
+        int i = lane + 32 * m;
+        if (i < k) part += Gs[q * k + i] * h[m];
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      const T grad = part - Ct[(size_t)j * k + q] + alpha;
+      const T step = T(1) / (scale * (Gs[q * k + q] + T(1)));
+#pragma unroll
+      for (int m = 0; m < NA; ++m)
+        if (lane + 32 * m == q) {
+          T v = h[m] - step * grad;
+          h[m] = v > T(0) ? v : T(0);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NA; ++m) {
+      int i = lane + 32 * m;
+      if (i < k) Ht[(size_t)j * k + i] = h[m];
+    }
+  }
+}
+
+template <typename T>
+static int pgd_t(const T* G, const T* Ct, long long n, int k, double alpha, int it, T* Ht, cudaStream_t st) {
+  size_t smem = (size_t)k * k * sizeof(T);
+  if (smem > (size_t)max_smem_optin()) return fail(ONMF_E_UNSUPPORTED, "pgd_sweep: Gram does not fit in shared memory");
+  const T scale = (T)sqrt((double)it + 10.0);
+  int threads = 256;
+  long long warps = n;
+  int grid = (int)cdiv<long long>(warps * 32, threads);
+  if (grid > 4 * num_sms()) grid = 4 * num_sms();
+  if (grid < 1) grid = 1;
+#define ONMF_PGD(NA)                                                                                 \
+  {                                                                                                  \
+    auto kern = pgd_sweep_kernel<T, NA>;                                                             \
+    ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    kern<<<grid, threads, smem, st>>>(G, Ct, n, k, (T)alpha, scale, Ht);                             \
+  }
+  if (k <= 32) ONMF_PGD(1)
+  else if (k <= 64) ONMF_PGD(2)
+  else if (k <= 128) ONMF_PGD(4)
+  else if (k <= 256) ONMF_PGD(8)
+  else if (k <= 512) ONMF_PGD(16)
+  else return fail(ONMF_E_UNSUPPORTED, "pgd_sweep: n_components > 512");
+#undef ONMF_PGD
+  ONMF_LAUNCH_CHECK("pgd_sweep_kernel");
+  return ONMF_OK;
+}
+
+template <typename TI, typename TO>
+static int transpose_t(const void* src, long long rows, long long cols, void* dst, cudaStream_t st) {
+  dim3 block(32, 8);
+  dim3 grid((unsigned)cdiv<long long>(cols, 32), (unsigned)cdiv<long long>(rows, 32));
+  if (grid.y > 65535) return fail(ONMF_E_UNSUPPORTED, "transpose: more than 2^21 rows; transpose the other way");
+  transpose_kernel<TI, TO><<<grid, block, 0, st>>>((const TI*)src, rows, cols, (TO*)dst);
+  ONMF_LAUNCH_CHECK("transpose_kernel");
+  return ONMF_OK;
+}
+
+}  // namespace onmf
+
+using namespace onmf;
+
+extern "C" int onmf_gather_patches(int dtype, const void* img, int H, int Wd, int C, const int32_t* coords, int64_t n,
+                                   int p, void* Xt, int64_t ld, void* stream) {
+  if (!img || !coords || !Xt || H <= 0 || Wd <= 0 || C <= 0 || p <= 0 || n < 0 || p > H || p > Wd || ld < (int64_t)p * p * C)
+    return fail(ONMF_E_ARG, "gather_patches: bad argument");
+  if (n == 0) return ONMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int threads = 256;
+  long long warps = n * p;
+  int grid = (int)cdiv<long long>(warps * 32, threads);
+  if (grid > 8 * num_sms()) grid = 8 * num_sms();
+  if (dtype == ONMF_F32) gather_patches_kernel<float><<<grid, threads, 0, st>>>((const float*)img, H, Wd, C, coords, n, p, (float*)Xt, ld);
+  else if (dtype == ONMF_F64) gather_patches_kernel<double><<<grid, threads, 0, st>>>((const double*)img, H, Wd, C, coords, n, p, (double*)Xt, ld);
+  else return fail(ONMF_E_ARG, "gather_patches: bad dtype");
+  ONMF_LAUNCH_CHECK("gather_patches_kernel");
+  return ONMF_OK;
+}
+
+extern "C" int onmf_gather_rows(int dtype, const void* pool, int64_t n_pool, int d, const int64_t* idx, int64_t n, void* Xt,
+                                void* stream) {
+  if (!pool || !idx || !Xt || d <= 0 || n < 0 || n_pool <= 0) return fail(ONMF_E_ARG, "gather_rows: bad argument");
+  if (n == 0) return ONMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int threads = 256;
+  int grid = (int)cdiv<long long>(n * 32, threads);
+  if (grid > 8 * num_sms()) grid = 8 * num_sms();
+  if (dtype == ONMF_F32) gather_rows_kernel<float><<<grid, threads, 0, st>>>((const float*)pool, d, (const long long*)idx, n, (float*)Xt);
+  else if (dtype == ONMF_F64) gather_rows_kernel<double><<<grid, threads, 0, st>>>((const double*)pool, d, (const long long*)idx, n, (double*)Xt);
+  else return fail(ONMF_E_ARG, "gather_rows: bad dtype");
+  ONMF_LAUNCH_CHECK("gather_rows_kernel");
+  return ONMF_OK;
+}
+
+extern "C" int onmf_transpose(int dtype_in, int dtype_out, const void* src, int64_t rows, int64_t cols, void* dst,
+                              void* stream) {
+  if (!src || !dst || rows < 0 || cols < 0) return fail(ONMF_E_ARG, "transpose: bad argument");
+  if (rows == 0 || cols == 0) return ONMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype_in == ONMF_F32 && dtype_out == ONMF_F32) return transpose_t<float, float>(src, rows, cols, dst, st);
+  if (dtype_in == ONMF_F64 && dtype_out == ONMF_F32) return transpose_t<double, float>(src, rows, cols, dst, st);
+  if (dtype_in == ONMF_F32 && dtype_out == ONMF_F64) return transpose_t<float, double>(src, rows, cols, dst, st);
+  if (dtype_in == ONMF_F64 && dtype_out == ONMF_F64) return transpose_t<double, double>(src, rows, cols, dst, st);
+  return fail(ONMF_E_ARG, "transpose: bad dtype");
+}
+
+extern "C" int onmf_pgd_sweep(int dtype, const void* G, const void* Ct, int64_t n, int k, double alpha, int it, void* Ht,
+                              void* stream) {
+  if (!G || !Ct || !Ht || n < 0 || k <= 0 || it < 0) return fail(ONMF_E_ARG, "pgd_sweep: bad argument");
+  if (n == 0) return ONMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == ONMF_F32) return pgd_t<float>((const float*)G, (const float*)Ct, n, k, alpha, it, (float*)Ht, st);
+  if (dtype == ONMF_F64) return pgd_t<double>((const double*)G, (const double*)Ct, n, k, alpha, it, (double*)Ht, st);
+  return fail(ONMF_E_ARG, "pgd_sweep: bad dtype");
+}

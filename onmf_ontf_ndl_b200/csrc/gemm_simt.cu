@@ -1,0 +1,280 @@
+// K2 / K4 -- dense products of the ONMF step, FP32/FP64 CUDA-core version.
+//
+//   cov   : Ct (n x k)       = Xt (n x d) . W (d x k)            [replaces dictionary @ X.T,
+//                                                                  sklearn/_dict_learning.py:426]
+//   gram  : G  (k x k)       = W^T W                              [_dict_learning.py:422]
+//   surrogate partial sums:  P (k x (k+d)) = [ Ht^T Ht | Ht^T Xt ] [np.dot(H1.T,H1), np.dot(H1.T,X.T),
+//                                                                  src/ontf.py:147-148]
+//   blend : A = (1-w) A + w P[:, :k],  B = (1-w) B + w P[:, k:]
+//
+// This file is the exact-FP32 (and FP64 parity-mode) path: register-tiled 128 x BN x 16 CTA tiles,
+// 8 x TN micro-tiles, split-K over the sample axis for the surrogate sums with a fixed-order
+// (deterministic) second-pass reduction.  The tensor-core (tcgen05, 3xTF32) versions of the two large
+// products live in gemm_tc.cu and are checked against this file.
+#include "common.cuh"
+
+namespace onmf {
+
+constexpr int BM = 128, BK = 16, NT = 256, TM = 8;
+
+// C[M x N] (+ split z) = op(A) . B ; A is (M x K) row-major (AKM=false) or (K x M) row-major (AKM=true);
+// B is (K x N) row-major with leading dim ldb; C row-major with leading dim ldc.
+template <typename T, int BN, bool AKM>
+__global__ void __launch_bounds__(NT) gemm_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb,
+                                                  T* __restrict__ C, int ldc, long long M, int N, long long K,
+                                                  long long kchunk, long long split_stride) {
+  constexpr int TN = BN / 16;
+  __shared__ T As[BK][BM + 4];
+  __shared__ T Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const long long kbeg = (long long)blockIdx.z * kchunk;
+  long long kend = kbeg + kchunk;
+  if (kend > K) kend = K;
+  T acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+
+  for (long long k0 = kbeg; k0 < kend; k0 += BK) {
+    if (AKM) {
+      // A tile BK x BM from rows k0.., contiguous along M
+      const int kk = tid >> 4, mm = (tid & 15) * 8;
+      const long long kr = k0 + kk;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        long long m = m0 + mm + e;
+        As[kk][mm + e] = (kr < kend && m < M) ? A[kr * lda + m] : T(0);
+      }
+    } else {
+      // A tile BM x BK from row-major (M x K): thread -> (row, 8 consecutive k)
+      const int row = tid >> 1, kq = (tid & 1) * 8;
+      const long long m = m0 + row;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        long long kr = k0 + kq + e;
+        As[kq + e][row] = (m < M && kr < kend) ? A[m * lda + kr] : T(0);
+      }
+    }
+    {
+      const int kk = tid >> 4, nn = (tid & 15) * TN;
+      const long long kr = k0 + kk;
+#pragma unroll
+      for (int e = 0; e < TN; ++e) {
+        int nc = n0 + nn + e;
+        Bs[kk][nn + e] = (kr < kend && nc < N) ? B[kr * ldb + nc] : T(0);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      T a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+  T* Cz = C + (size_t)blockIdx.z * split_stride;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    long long m = m0 + ty * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int nc = n0 + tx * TN + j;
+      if (nc < N) Cz[m * ldc + nc] = acc[i][j];
+    }
+  }
+}
+
+// out[i] = sum_z part[z][i] in fixed order z = 0..splits-1
+template <typename T>
+__global__ void split_reduce_kernel(const T* __restrict__ part, int splits, long long count, long long stride,
+                                    T* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  T s = T(0);
+  for (int z = 0; z < splits; ++z) s += part[(size_t)z * stride + i];
+  out[i] = s;
+}
+
+template <typename T>
+__global__ void blend_kernel(const T* __restrict__ P, int k, int d, T w, T* __restrict__ A, T* __restrict__ B) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long tot = (long long)k * (k + d);
+  if (i >= tot) return;
+  int r = (int)(i / (k + d)), c = (int)(i - (long long)r * (k + d));
+  T p = P[i];
+  T om = T(1) - w;
+  if (c < k) {
+    size_t o = (size_t)r * k + c;
+    A[o] = om * A[o] + w * p;
+  } else {
+    size_t o = (size_t)r * d + (c - k);
+    B[o] = om * B[o] + w * p;
+  }
+}
+
+template <typename T>
+__global__ void axpby_kernel(long long count, T a, const T* __restrict__ x, T b, T* __restrict__ y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) y[i] = a * x[i] + b * y[i];
+}
+
+template <typename T, bool AKM>
+static int launch_gemm(const T* A, int lda, const T* B, int ldb, T* C, int ldc, long long M, int N, long long K,
+                       int splits, long long split_stride, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return ONMF_OK;
+  long long kchunk = round_up<long long>(cdiv<long long>(K, splits), BK);
+  if (kchunk < BK) kchunk = BK;
+  dim3 block(NT);
+  if (N <= 32) {
+    dim3 grid((unsigned)cdiv<long long>(M, BM), (unsigned)cdiv(N, 32), splits);
+    gemm_kernel<T, 32, AKM><<<grid, block, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kchunk, split_stride);
+  } else if (N <= 64) {
+    dim3 grid((unsigned)cdiv<long long>(M, BM), (unsigned)cdiv(N, 64), splits);
+    gemm_kernel<T, 64, AKM><<<grid, block, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kchunk, split_stride);
+  } else {
+    dim3 grid((unsigned)cdiv<long long>(M, BM), (unsigned)cdiv(N, 128), splits);
+    gemm_kernel<T, 128, AKM><<<grid, block, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kchunk, split_stride);
+  }
+  ONMF_LAUNCH_CHECK("gemm_kernel");
+  return ONMF_OK;
+}
+
+static int pick_splits(long long n, int k, int d) {
+  // enough CTAs to fill the GPU: tiles(M=k, N=k+d) * splits >= 2 * SMs, each split >= 256 samples
+  long long tiles = cdiv(k, BM) * (cdiv(k, 128) + cdiv(d, 128));
+  long long want = cdiv<long long>(2LL * num_sms(), tiles);
+  long long cap = cdiv<long long>(n, 256);
+  long long s = want < cap ? want : cap;
+  if (s < 1) s = 1;
+  if (s > 256) s = 256;
+  return (int)s;
+}
+
+template <typename T>
+static int surrogate_partial_t(const T* Ht, const T* Xt, long long n, int k, int d, T* P, T* ws, cudaStream_t st) {
+  const int splits = pick_splits(n, k, d);
+  const long long ldp = k + d;
+  const long long stride = (long long)k * ldp;
+  T* dst = splits == 1 ? P : ws;
+  // [Ht^T Ht] -> columns 0..k-1 ; [Ht^T Xt] -> columns k..k+d-1 of the packed (k x (k+d)) buffer
+  int rc = launch_gemm<T, true>(Ht, k, Ht, k, dst, (int)ldp, k, k, n, splits, stride, st);
+  if (rc) return rc;
+  rc = launch_gemm<T, true>(Ht, k, Xt, d, dst + k, (int)ldp, k, d, n, splits, stride, st);
+  if (rc) return rc;
+  if (splits > 1) {
+    int threads = 256;
+    split_reduce_kernel<T><<<(unsigned)cdiv<long long>(stride, threads), threads, 0, st>>>(ws, splits, stride, stride, P);
+    ONMF_LAUNCH_CHECK("split_reduce_kernel");
+  }
+  return ONMF_OK;
+}
+
+}  // namespace onmf
+
+using namespace onmf;
+
+extern "C" int onmf_gram(int dtype, const void* W, int d, int k, void* G, void* stream) {
+  if (!W || !G || d <= 0 || k <= 0) return fail(ONMF_E_ARG, "gram: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == ONMF_F32) return launch_gemm<float, true>((const float*)W, k, (const float*)W, k, (float*)G, k, k, k, d, 1, 0, st);
+  if (dtype == ONMF_F64) return launch_gemm<double, true>((const double*)W, k, (const double*)W, k, (double*)G, k, k, k, d, 1, 0, st);
+  return fail(ONMF_E_ARG, "gram: bad dtype");
+}
+
+extern "C" int onmf_cov(int dtype, const void* Xt, int64_t n, int d, const void* W, int k, void* Ct, void* stream) {
+  if (!Xt || !W || !Ct || n < 0 || d <= 0 || k <= 0) return fail(ONMF_E_ARG, "cov: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == ONMF_F32) return launch_gemm<float, false>((const float*)Xt, d, (const float*)W, k, (float*)Ct, k, n, k, d, 1, 0, st);
+  if (dtype == ONMF_F64) return launch_gemm<double, false>((const double*)Xt, d, (const double*)W, k, (double*)Ct, k, n, k, d, 1, 0, st);
+  return fail(ONMF_E_ARG, "cov: bad dtype");
+}
+
+extern "C" size_t onmf_surrogate_workspace(int dtype, int64_t n, int k, int d) {
+  if (n < 0 || k <= 0 || d <= 0) return 0;
+  size_t tsz = dtype == ONMF_F64 ? 8 : 4;
+  return (size_t)pick_splits(n, k, d) * (size_t)k * (size_t)(k + d) * tsz + 256;
+}
+
+extern "C" int onmf_surrogate_partial(int dtype, const void* Ht, const void* Xt, int64_t n, int k, int d, void* P,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (!Ht || !Xt || !P || n < 0 || k <= 0 || d <= 0) return fail(ONMF_E_ARG, "surrogate_partial: bad argument");
+  if (!workspace || workspace_bytes < onmf_surrogate_workspace(dtype, n, k, d))
+    return fail(ONMF_E_WORKSPACE, "surrogate_partial: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    ONMF_CUDA(cudaMemsetAsync(P, 0, (size_t)k * (k + d) * (dtype == ONMF_F64 ? 8 : 4), st));
+    return ONMF_OK;
+  }
+  if (dtype == ONMF_F32) return surrogate_partial_t<float>((const float*)Ht, (const float*)Xt, n, k, d, (float*)P, (float*)workspace, st);
+  if (dtype == ONMF_F64) return surrogate_partial_t<double>((const double*)Ht, (const double*)Xt, n, k, d, (double*)P, (double*)workspace, st);
+  return fail(ONMF_E_ARG, "surrogate_partial: bad dtype");
+}
+
+extern "C" int onmf_xxt_partial(int dtype, const void* Xt, int64_t n, int d, void* P2, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (!Xt || !P2 || n < 0 || d <= 0) return fail(ONMF_E_ARG, "xxt_partial: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t tsz = dtype == ONMF_F64 ? 8 : 4;
+  if (n == 0) {
+    ONMF_CUDA(cudaMemsetAsync(P2, 0, (size_t)d * d * tsz, st));
+    return ONMF_OK;
+  }
+  long long tiles = cdiv(d, BM) * cdiv(d, 128);
+  long long want = cdiv<long long>(2LL * num_sms(), tiles);
+  long long cap = cdiv<long long>(n, 256);
+  int splits = (int)(want < cap ? want : cap);
+  if (splits < 1) splits = 1;
+  long long stride = (long long)d * d;
+  if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * stride * tsz)) splits = 1;
+  int rc;
+  if (dtype == ONMF_F32) {
+    float* dst = splits == 1 ? (float*)P2 : (float*)workspace;
+    rc = launch_gemm<float, true>((const float*)Xt, d, (const float*)Xt, d, dst, d, d, d, n, splits, stride, st);
+    if (!rc && splits > 1) split_reduce_kernel<float><<<(unsigned)cdiv<long long>(stride, 256), 256, 0, st>>>((float*)workspace, splits, stride, stride, (float*)P2);
+  } else if (dtype == ONMF_F64) {
+    double* dst = splits == 1 ? (double*)P2 : (double*)workspace;
+    rc = launch_gemm<double, true>((const double*)Xt, d, (const double*)Xt, d, dst, d, d, d, n, splits, stride, st);
+    if (!rc && splits > 1) split_reduce_kernel<double><<<(unsigned)cdiv<long long>(stride, 256), 256, 0, st>>>((double*)workspace, splits, stride, stride, (double*)P2);
+  } else {
+    return fail(ONMF_E_ARG, "xxt_partial: bad dtype");
+  }
+  if (rc) return rc;
+  ONMF_LAUNCH_CHECK("xxt_partial");
+  return ONMF_OK;
+}
+
+extern "C" int onmf_surrogate_blend(int dtype, const void* P, int k, int d, double w, void* A, void* B, void* stream) {
+  if (!P || !A || !B || k <= 0 || d <= 0) return fail(ONMF_E_ARG, "surrogate_blend: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long tot = (long long)k * (k + d);
+  unsigned grid = (unsigned)cdiv<long long>(tot, 256);
+  if (dtype == ONMF_F32) blend_kernel<float><<<grid, 256, 0, st>>>((const float*)P, k, d, (float)w, (float*)A, (float*)B);
+  else if (dtype == ONMF_F64) blend_kernel<double><<<grid, 256, 0, st>>>((const double*)P, k, d, w, (double*)A, (double*)B);
+  else return fail(ONMF_E_ARG, "surrogate_blend: bad dtype");
+  ONMF_LAUNCH_CHECK("blend_kernel");
+  return ONMF_OK;
+}
+
+extern "C" int onmf_axpby(int dtype, int64_t count, double a, const void* x, double b, void* y, void* stream) {
+  if (!x || !y || count < 0) return fail(ONMF_E_ARG, "axpby: bad argument");
+  if (count == 0) return ONMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned grid = (unsigned)cdiv<long long>(count, 256);
+  if (dtype == ONMF_F32) axpby_kernel<float><<<grid, 256, 0, st>>>(count, (float)a, (const float*)x, (float)b, (float*)y);
+  else if (dtype == ONMF_F64) axpby_kernel<double><<<grid, 256, 0, st>>>(count, a, (const double*)x, b, (double*)y);
+  else return fail(ONMF_E_ARG, "axpby: bad dtype");
+  ONMF_LAUNCH_CHECK("axpby_kernel");
+  return ONMF_OK;
+}

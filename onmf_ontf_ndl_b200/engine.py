@@ -1,0 +1,187 @@
+"""Device-resident engine for the online NMF/NTF dictionary-learning step.
+
+One `OnmfEngine` owns the replicated state (W, A, B[, C]) of one rank and runs, per minibatch,
+
+    main stream :  G = W^T W ; Ct = Xt W ; Ht = lasso_lars(G, Ct) ; P = [Ht^T Ht | Ht^T Xt]
+    side stream :  (all-reduce P of the PREVIOUS step) ; A,B <- (1-w) A,B + w P ; W' = BCD(W; A_prev, B_prev)
+
+which is the reference's `step` (src/ontf.py:117-154): code with the current dictionary, update the
+aggregates, and update the dictionary with the OLD aggregates (src/ontf.py:151).  That one-step lag is
+what lets the side stream (and, across GPUs, the NCCL all-reduce of the k x (k+d) partial sums) overlap
+the next minibatch's sparse coding.  Minibatch columns are sharded across ranks; W, A, B are replicated
+and stay bit-identical because every rank runs the same deterministic dictionary update on the same
+all-reduced aggregates.
+
+All arithmetic is in the hand-written kernels of libonmf_b200.so (see _lib.py); torch only owns
+memory, streams, events and the process group.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+class OnmfEngine:
+    def __init__(self, d: int, k: int, alpha: float = 1.0, beta: Optional[float] = None,
+                 dtype: torch.dtype = torch.float32, device=None, max_iter: int = 1000,
+                 process_group=None, track_C: bool = False, collect_stats: bool = False):
+        if not torch.cuda.is_available():
+            raise _lib.OnmfKernelError("OnmfEngine needs a CUDA device (there is no CPU path)")
+        _lib.load()
+        self.d, self.k = int(d), int(k)
+        self.alpha = float(alpha)
+        self.beta = 1.0 if beta is None else float(beta)
+        self.dtype = dtype
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.max_iter = int(max_iter)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.track_C = bool(track_C)
+        dev, dt_ = self.device, dtype
+        self.W = torch.zeros(d, k, dtype=dt_, device=dev)
+        self.W_next = torch.zeros(d, k, dtype=dt_, device=dev)
+        self.A = torch.zeros(k, k, dtype=dt_, device=dev)
+        self.B = torch.zeros(k, d, dtype=dt_, device=dev)
+        self.C = torch.zeros(d, d, dtype=dt_, device=dev) if track_C else None
+        self.G = torch.empty(k, k, dtype=dt_, device=dev)
+        self.P = [torch.zeros(k, k + d, dtype=dt_, device=dev) for _ in range(2)]
+        self.P2 = torch.zeros(d, d, dtype=dt_, device=dev) if track_C else None
+        self._cap = 0
+        self.Ct = self.Ht = self._ws_lars = self._ws_sur = None
+        self.stats = torch.zeros(len(_lib.STATS_FIELDS), dtype=torch.int64, device=dev) if collect_stats else None
+        self.main = torch.cuda.current_stream(dev)
+        self.side = torch.cuda.Stream(dev)
+        self._ev_P = torch.cuda.Event()        # P[cur] complete on main
+        self._ev_W = torch.cuda.Event()        # W (for the next coding) complete on side
+        self._ev_code = torch.cuda.Event()     # main finished reading W / Xt of the current step
+        self._cur = 0
+        self.launches = 0
+
+    # ------------------------------------------------------------------ state
+    def set_state(self, W, A=None, B=None, C=None):
+        self.flush()
+        self.W.copy_(torch.as_tensor(W).to(self.device, self.dtype))
+        for dst, src in ((self.A, A), (self.B, B), (self.C, C)):
+            if dst is None:
+                continue
+            if src is None:
+                dst.zero_()
+            else:
+                dst.copy_(torch.as_tensor(src).to(self.device, self.dtype))
+
+    def _reserve(self, n):
+        if n <= self._cap:
+            return
+        dev, dt_ = self.device, self.dtype
+        self._cap = int(n)
+        self.Ct = torch.empty(self._cap, self.k, dtype=dt_, device=dev)
+        self.Ht = torch.empty(self._cap, self.k, dtype=dt_, device=dev)
+        self._ws_lars = torch.empty(_lib.lasso_lars_workspace(dt_, self.k, self._cap), dtype=torch.uint8, device=dev)
+        nbytes = _lib.surrogate_workspace(dt_, self._cap, self.k, self.d)
+        if self.track_C:
+            nbytes = max(nbytes, 64 * self.d * self.d * self.W.element_size() + 256)
+        self._ws_sur = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+    def _stats_ptr(self):
+        return self.stats if self.stats is not None else None
+
+    # ------------------------------------------------------------------ coding only
+    def sparse_code(self, Xt: torch.Tensor, W: Optional[torch.Tensor] = None, alpha=None, out=None):
+        """Ht (n x k) = positive lasso_lars codes of the rows of Xt (n x d) against W (default: current)."""
+        n = Xt.shape[0]
+        self._reserve(n)
+        W = self.W if W is None else W
+        Ct = self.Ct[:n]
+        Ht = self.Ht[:n] if out is None else out
+        _lib.gram(W, self.G)
+        _lib.cov(Xt, W, Ct)
+        _lib.lasso_lars(self.G, Ct, self.d, self.alpha if alpha is None else alpha, Ht, self._ws_lars,
+                        max_iter=self.max_iter, stats=self._stats_ptr())
+        self.launches += 4
+        return Ht
+
+    # ------------------------------------------------------------------ one online step
+    def step_with_codes(self, Xt, Ht, t):
+        """Same as step() but with externally computed codes Ht (n x k), e.g. from the PGD coder."""
+        return self.step(Xt, t, codes=Ht)
+
+    def step(self, Xt: torch.Tensor, t: float, codes: Optional[torch.Tensor] = None):
+        """One minibatch: Xt (n_local x d) are THIS rank's columns of the minibatch, t the step index
+        (w = t^-beta).  Returns the local codes Ht (view, valid until the next call)."""
+        main, side = self.main, self.side
+        n = Xt.shape[0]
+        self._reserve(max(n, 1))
+        w = float(t) ** (-self.beta)
+        cur = self._cur
+        # side stream: dictionary update for this step with the OLD aggregates (src/ontf.py:151).  It is
+        # queued behind the previous step's all-reduce + blend (same stream), and must not overwrite the
+        # buffer the previous coding was still reading.
+        with torch.cuda.stream(side):
+            side.wait_event(self._ev_code)
+            _lib.update_dict(self.W, self.A, self.B, self.W_next, stream=side)
+            self._ev_W.record(side)
+            self.launches += 1
+        # main stream: code this minibatch with W_{t-1}
+        Ht = self.Ht[:n] if codes is None else codes
+        if self.track_C:
+            main.wait_stream(side)                  # P2 is single-buffered
+        if n > 0:
+            if codes is None:
+                Ct = self.Ct[:n]
+                _lib.gram(self.W, self.G, stream=main)
+                _lib.cov(Xt, self.W, Ct, stream=main)
+                _lib.lasso_lars(self.G, Ct, self.d, self.alpha, Ht, self._ws_lars, max_iter=self.max_iter,
+                                stats=self._stats_ptr(), stream=main)
+            _lib.surrogate_partial(Ht, Xt, self.P[cur], self._ws_sur, stream=main)
+            self.launches += 7
+            if self.track_C:
+                _lib.xxt_partial(Xt, self.P2, self._ws_sur, stream=main)
+                self.launches += 2
+        else:
+            with torch.cuda.stream(main):
+                self.P[cur].zero_()
+                if self.track_C:
+                    self.P2.zero_()
+        self._ev_P.record(main)
+        self._ev_code.record(main)
+        # side stream: all-reduce the packed partial sums and blend them into A, B.  Nothing on the main
+        # stream waits for this: it overlaps the NEXT minibatch's coding and is only consumed by the next
+        # dictionary update (queued behind it on this stream).
+        with torch.cuda.stream(side):
+            side.wait_event(self._ev_P)
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(self.P[cur], group=self.pg)
+                if self.track_C:
+                    dist.all_reduce(self.P2, group=self.pg)
+            _lib.surrogate_blend(self.P[cur], w, self.A, self.B, stream=side)
+            self.launches += 1
+            if self.track_C:
+                _lib.axpby(w, self.P2, 1.0 - w, self.C, stream=side)
+                self.launches += 1
+        # the next coding needs W_t (= W_next): wait for the dictionary update only
+        main.wait_event(self._ev_W)
+        self.W, self.W_next = self.W_next, self.W
+        self._cur ^= 1
+        return Ht
+
+    def flush(self):
+        """Make W, A, B (C) visible to the current stream / host."""
+        self.main.wait_stream(self.side)
+
+    def state(self):
+        self.flush()
+        return self.W, self.A, self.B, self.C
+
+    def read_stats(self):
+        if self.stats is None:
+            return None
+        torch.cuda.synchronize(self.device)
+        vals = self.stats.cpu().tolist()
+        return dict(zip(_lib.STATS_FIELDS, vals))

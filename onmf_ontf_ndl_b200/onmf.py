@@ -1,0 +1,242 @@
+"""Online_NMF and update_code_within_radius -- drop-ins for the reference's src/onmf.py on B200.
+
+The reference tree ships three mutually incompatible generations of this class; this
+class accepts the union of their constructor arguments:
+
+    Online_NMF(X, n_components=100, iterations=500, batch_size=20,
+               ini_dict=None, ini_A=None, ini_B=None, ini_C=None,     # what ALL shipped drivers pass
+               ini_agg=None,                                          # shipped src/onmf.py:28
+               history=0, alpha=None, beta=None, subsample=False)
+      .train_dict(full_code=False)
+            -> (W, At, Bt, Ct, H)        driver style (image_reconstruction.py:298, ising_reconstruction.py:127,
+                                         network_reconstruction_nx.py:364)   [default]
+            -> (W, [A, B(, C)], code)    shipped style (src/onmf.py:226)     [when ini_agg is given or
+                                                                              compat="shipped_onmf"]
+      .sparse_code(X, W) -> H (r x n)    src/onmf.py:51-90
+      .update_dict(W, A, B) -> W1        src/onmf.py:92-116
+      .step(X, aggregates, W, t) -> (H1, aggregates1, W1)            src/onmf.py:119-167
+      .history, .code
+
+Default semantics are the `ontf.py` / paper recursion (aggregates accumulate across steps; sparse coding
+is the positive lasso -- BASELINE.json north_star: "a batched nonnegative-lasso kernel replaces
+sparse_code").  `compat="shipped_onmf"` reproduces the literal shipped file instead: random-H0
+projected-gradient coder (src/onmf.py:87, :233-271) and the aggregate re-binding of src/onmf.py:217.
+alpha=None means 0 here (src/onmf.py:82-84).
+
+Extra keywords (not in the reference): precision ("fp32" | "fp64"), coder ("lasso_lars" | "pgd"),
+compat (None | "shipped_onmf"), track_C (maintain the d x d aggregate C even without full_code).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _host, _lib
+from .engine import OnmfEngine
+
+DEBUG = False
+
+
+class Online_NMF():
+
+    def __init__(self,
+                 X,
+                 n_components=100,
+                 iterations=500,
+                 batch_size=20,
+                 ini_dict=None,
+                 ini_A=None,
+                 ini_B=None,
+                 ini_C=None,
+                 ini_agg=None,
+                 history=0,
+                 alpha=None,
+                 beta=None,
+                 subsample=False,
+                 precision=None,
+                 coder=None,
+                 compat=None,
+                 track_C=None):
+        self.X = X
+        self.n_components = n_components
+        self.batch_size = batch_size
+        self.iterations = iterations
+        self.subsample = subsample
+        self.initial_dict = ini_dict
+        self.initial_agg = ini_agg
+        if ini_agg is None and (ini_A is not None or ini_B is not None):
+            agg = [ini_A, ini_B]
+            if ini_C is not None:
+                agg.append(ini_C)
+            self.initial_agg = agg
+        self._shipped_return = (ini_agg is not None) or (compat == "shipped_onmf")
+        self.history = history
+        self.alpha = alpha
+        self.beta = beta
+        self.code = np.zeros(shape=(n_components, X.shape[1]))
+        if compat not in (None, "shipped_onmf"):
+            raise ValueError("compat must be None or 'shipped_onmf'")
+        self.compat = compat
+        self.coder = coder if coder is not None else ("pgd" if compat == "shipped_onmf" else "lasso_lars")
+        if self.coder not in ("lasso_lars", "pgd"):
+            raise ValueError("coder must be 'lasso_lars' or 'pgd'")
+        self.precision = precision
+        self._dtype = _host.torch_dtype(precision)
+        self.track_C = track_C
+        self.lars_stats = None
+
+    def _alpha(self):
+        return 0 if self.alpha is None else self.alpha        # src/onmf.py:82-84
+
+    # -- coders ----------------------------------------------------------------------------------
+    def _code_device(self, eng, Xt, Wd):
+        """Ht (n x r) on device with the configured coder."""
+        if self.coder == "lasso_lars":
+            return eng.sparse_code(Xt, Wd, alpha=self._alpha())
+        n, r = Xt.shape[0], Wd.shape[1]
+        H0 = np.random.rand(r, n)                              # src/onmf.py:245-246 (global host RNG)
+        Ht = _host.to_device(np.ascontiguousarray(H0.T), self._dtype, Xt.device)
+        return _pgd_device(Xt, Wd, Ht, self._alpha(), 10, 0.01)   # src/onmf.py:87
+
+    def sparse_code(self, X, W):
+        """H (r x n) for data X (d x n) and dictionary W (d x r)."""
+        dev = _host.device()
+        Xt = _host.to_sample_major(X, self._dtype, dev)
+        Wd = _host.to_device(W, self._dtype, dev)
+        eng = OnmfEngine(Wd.shape[0], Wd.shape[1], alpha=self._alpha(), beta=self.beta, dtype=self._dtype,
+                         device=dev, collect_stats=True)
+        Ht = self._code_device(eng, Xt, Wd)
+        self.lars_stats = eng.read_stats()
+        return _host.from_sample_major(Ht)
+
+    def update_dict(self, W, A, B):
+        dev = _host.device()
+        Wd = _host.to_device(W, self._dtype, dev)
+        out = torch.empty_like(Wd)
+        _lib.update_dict(Wd, _host.to_device(A, self._dtype, dev), _host.to_device(B, self._dtype, dev), out)
+        return _host.to_numpy(out)
+
+    def step(self, X, aggregates, W, t):
+        """src/onmf.py:119-167 on host arrays: returns (H1 (r x n), [A1, B1(, C1)], W1)."""
+        dev = _host.device()
+        d, r = np.shape(W)
+        has_C = len(aggregates) == 3
+        eng = OnmfEngine(d, r, alpha=self._alpha(), beta=self.beta, dtype=self._dtype, device=dev, track_C=has_C)
+        eng.set_state(W, aggregates[0], aggregates[1], aggregates[2] if has_C else None)
+        Xt = _host.to_sample_major(X, self._dtype, dev)
+        H1 = self._step_device(eng, Xt, float(t))
+        Wd, Ad, Bd, Cd = eng.state()
+        out = [_host.to_numpy(Ad), _host.to_numpy(Bd)]
+        if has_C:
+            out.append(_host.to_numpy(Cd))
+        self.history = np.float64(t) + 1
+        return _host.from_sample_major(H1), out, _host.to_numpy(Wd)
+
+    def _step_device(self, eng, Xt, t):
+        if self.coder == "lasso_lars":
+            return eng.step(Xt, t)
+        Ht = self._code_device(eng, Xt, eng.W)
+        return eng.step_with_codes(Xt, Ht, t)
+
+    # -- training loop ---------------------------------------------------------------------------
+    def train_dict(self, full_code=False):
+        dev = _host.device()
+        X = np.asarray(self.X)
+        d, n = X.shape
+        r = self.n_components
+        code = self.code
+        agg0 = self.initial_agg
+        want_C = bool(full_code) or (self.track_C if self.track_C is not None else not self._shipped_return) \
+            or (agg0 is not None and len(agg0) == 3)
+
+        if self.initial_dict is None:
+            W = np.random.rand(d, r)                    # src/onmf.py:190
+            A0 = B0 = C0 = None
+        else:
+            W = self.initial_dict
+            A0 = agg0[0] if agg0 is not None else None
+            B0 = agg0[1] if agg0 is not None else None
+            C0 = agg0[2] if (agg0 is not None and len(agg0) == 3) else None
+        t0 = self.history
+
+        pool = _host.to_sample_major(X, self._dtype, dev)        # (n x d)
+        eng = OnmfEngine(d, r, alpha=self._alpha(), beta=self.beta, dtype=self._dtype, device=dev,
+                         track_C=want_C, collect_stats=True)
+        eng.set_state(W, A0, B0, C0)
+        shipped = self.compat == "shipped_onmf"
+        if shipped:
+            A_init, B_init = eng.A.clone(), eng.B.clone()
+            C_init = eng.C.clone() if want_C else None
+        Xb = torch.empty(self.batch_size if self.subsample else 0, d, dtype=self._dtype, device=dev)
+        for i in np.arange(1, self.iterations):
+            idx = np.arange(n)
+            if self.subsample:
+                idx = np.random.randint(n, size=self.batch_size)          # src/onmf.py:212
+                _lib.gather_rows(pool, torch.from_numpy(idx.astype(np.int64)).to(dev), Xb)
+                Xt = Xb
+            else:
+                Xt = pool
+            if shipped:
+                # src/onmf.py:217 re-binds the aggregates to the arrays fixed before the loop
+                eng.flush()
+                eng.A.copy_(A_init)
+                eng.B.copy_(B_init)
+                if want_C:
+                    eng.C.copy_(C_init)
+            Ht = self._step_device(eng, Xt, float(t0 + i))
+            self.history = np.float64(t0 + i) + 1
+            code[:, idx] += _host.from_sample_major(Ht)               # src/onmf.py:221
+        Wd, Ad, Bd, Cd = eng.state()
+        self.lars_stats = eng.read_stats()
+        Wn, An, Bn = _host.to_numpy(Wd), _host.to_numpy(Ad), _host.to_numpy(Bd)
+        Cn = _host.to_numpy(Cd) if want_C else None
+        if self._shipped_return:
+            aggregates = [An, Bn]
+            if Cn is not None and (full_code or (agg0 is not None and len(agg0) == 3)):
+                aggregates.append(Cn)
+            return Wn, aggregates, code
+        return Wn, An, Bn, Cn, code
+
+
+####################################
+# custom sparsecoder
+
+def _spectral_norm(M):
+    return torch.linalg.matrix_norm(M, ord=2)
+
+
+def _pgd_device(Xt, Wd, Ht, alpha, sub_iter, stopping_diff):
+    """Outer loop of the reference's projected-gradient coder (src/onmf.py:252-268, r=None) around the
+    onmf_pgd_sweep kernel.  The stopping test needs two spectral norms per outer iteration
+    (np.linalg.norm(., 2), src/onmf.py:265); they are taken with torch.linalg on the device."""
+    k = Wd.shape[1]
+    G = torch.empty(k, k, dtype=Wd.dtype, device=Wd.device)
+    Ct = torch.empty(Xt.shape[0], k, dtype=Wd.dtype, device=Wd.device)
+    _lib.gram(Wd, G)
+    _lib.cov(Xt, Wd, Ct)
+    i, dist = 0, 1.0
+    while i < sub_iter and dist > stopping_diff:
+        H_old = Ht.clone()
+        _lib.pgd_sweep(G, Ct, alpha, i, Ht)
+        dist = float(_spectral_norm(Ht - H_old) / _spectral_norm(H_old))
+        i += 1
+    return Ht
+
+
+def update_code_within_radius(X, W, H0=None, r=None, alpha=0, sub_iter=10, stopping_diff=0.1, precision=None):
+    """Row-wise projected gradient descent for argmin_H |X - WH|^2/2 + alpha|H|_1, H >= 0
+    (reference src/onmf.py:233-271).  Returns H (r x n) as numpy float64."""
+    if r is not None:
+        raise NotImplementedError("radius-restricted coding (r is not None) is not on the B200 hot path; "
+                                  "no shipped driver uses it (image_reconstruction.py:384 passes r=None)")
+    dev = _host.device()
+    dtype = _host.torch_dtype(precision)
+    X = np.asarray(X)
+    W = np.asarray(W)
+    if H0 is None:
+        H0 = np.random.rand(W.shape[1], X.shape[1])              # src/onmf.py:245-246
+    Xt = _host.to_sample_major(X, dtype, dev)
+    Wd = _host.to_device(W, dtype, dev)
+    Ht = _host.to_device(np.ascontiguousarray(np.asarray(H0).T), dtype, dev)
+    Ht = _pgd_device(Xt, Wd, Ht, alpha, sub_iter, stopping_diff)
+    return _host.from_sample_major(Ht)
