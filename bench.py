@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- ONMF samples/s (code + surrogate + dictionary update) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg5]
+
+Workload (BASELINE.json configs[4], the one the metric is quoted on): synthetic nonnegative data,
+d=1024 (32x32 patches), k=256 atoms, global minibatch 262,144 columns sharded by columns over the N GPUs
+(strong scaling: the global minibatch is fixed), alpha=1, beta=1, fp32 production mode.  A "step" is one
+pass of the hot path over one minibatch: K1 gather of a freshly resampled minibatch from the resident
+pool, K2 Gram+covariance, K3 LARS-lasso coding, K4 surrogate partial sums (+ NCCL all-reduce of the packed
+k x (k+d) buffer at N>1) + blend, K5 dictionary update.
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM; `e2e` = the
+same steps fed from pinned HOST memory through OnmfEngine.step_host (H2D of every minibatch and D2H of the
+updated dictionary inside the timed region).  `roofline` describes the dominant kernel (the LARS coder,
+timed live with CUDA events on its launch stream), `cpu_baseline` the reference CPU path (numpy + sklearn
+lasso_lars, the oracle port) on a bounded column sample on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (d, k, global minibatch, alpha)
+    "cfg1": (100, 25, 1000, 1.0),
+    "cfg2": (300, 49, 4000, 1.0),
+    "cfg3": (441, 25, 10000, 1.0),
+    "cfg4": (400, 100, 16384, 1.0),
+    "cfg5": (1024, 256, 262144, 1.0),
+}
+METRIC = "ONMF samples/sec (code+surrogate+dict update)"
+UNIT = "samples/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML; same fields as the
+    nvidia-smi line of B200_PROFILING.md)."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_step(d, k, alpha, cols, seed=0, steps=1, warmup=0):
+    """The reference's CPU step (numpy + scikit-learn positive lasso_lars + A,B recursion + update_dict) via the
+    oracle port (oracle/onmf_oracle.py, coder='sklearn' = the dependency called like src/ontf.py:79-86) on a
+    bounded sample of `cols` columns of the same synthetic workload.  Returns (samples/s, seconds per step)."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import onmf_oracle as O
+    rng = np.random.RandomState(seed)
+    X = rng.rand(d, cols)
+    W = rng.rand(d, k)
+    A, B = np.zeros((k, k)), np.zeros((k, d))
+    # one untimed dictionary sweep so the timed steps see a unit-ball dictionary like every step after the first
+    W = O.update_dict(W, A, B)
+    times = []
+    for t in range(1, warmup + steps + 1):
+        t0 = time.perf_counter()
+        H, A, B, W = O.step(X, A, B, W, float(t), alpha, None, coder="sklearn")
+        el = time.perf_counter() - t0
+        if t > warmup:
+            times.append(el)
+    sec = float(np.mean(times))
+    return cols / sec, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    d, k, n_global, alpha = WORKLOADS[args.workload]
+    # bounded sample: ~7.6 ms per cfg5 column on one core -> keep the whole run near two minutes
+    per_col_ms = {"cfg5": 7.6, "cfg4": 3.2, "cfg3": 2.1, "cfg2": 2.2, "cfg1": 1.05}[args.workload]
+    cols = args.cpu_cols or int(max(64, min(n_global, 110e3 / per_col_ms / (args.steps + args.warmup))))
+    val, sec = cpu_reference_step(d, k, alpha, cols, steps=args.steps, warmup=args.warmup)
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        blas_threads = None
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: synthetic U[0,1) d=%d k=%d global minibatch %d alpha=%g" % (args.workload, d, k, n_global, alpha),
+                   "d": d, "k": k, "global_batch": n_global},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "%d of %d columns per step, numpy+scikit-learn lasso_lars (the reference's CPU path via the "
+                                   "oracle port; per-sample LARS loop is single-threaded, BLAS threads=%s, host cpus=%s)"
+                                   % (cols, n_global, blas_threads, os.cpu_count())},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from onmf_ontf_ndl_b200 import OnmfEngine, _lib
+    from onmf_ontf_ndl_b200.parallel import init_from_env, shard_range
+
+    rank, world, local = init_from_env("nccl")
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    d, k, n_global, alpha = WORKLOADS[args.workload]
+    lo, hi = shard_range(n_global, world, rank)
+    n = hi - lo
+    dt = torch.float32
+    K, Wm = args.steps, args.warmup
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    pool = torch.rand(n, d, dtype=dt, device=dev, generator=gen)       # this rank's resident column pool
+    gw = torch.Generator(device=dev)
+    gw.manual_seed(0)                                                   # same W0 on every rank
+    W0 = torch.rand(d, k, dtype=dt, device=dev, generator=gw)
+    eng = OnmfEngine(d, k, alpha=alpha, dtype=dt, device=dev, process_group=dist.group.WORLD if world > 1 else None,
+                     collect_stats=True)
+    eng.set_state(W0)
+    Xb = torch.empty(n, d, dtype=dt, device=dev)
+    main = eng.main
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_step(t):
+        idx = torch.randint(0, n, (n,), device=dev, generator=gen)     # fresh minibatch: resample the pool (with replacement)
+        _lib.gather_rows(pool, idx, Xb)
+        eng.step(Xb, float(t))
+
+    t = 0
+    for _ in range(Wm):
+        t += 1
+        one_step(t)
+    barrier()
+    if eng.stats is not None:
+        eng.stats.zero_()
+    launches0 = eng.launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lars_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    # wrap the LARS launch with events on its launch stream (the engine's main stream)
+    orig_lars = _lib.lasso_lars
+    counter = {"i": 0}
+
+    def timed_lars(*a, **kw):
+        i = counter["i"]
+        if i < K:
+            lars_ev[i][0].record(main)
+        r = orig_lars(*a, **kw)
+        if i < K:
+            lars_ev[i][1].record(main)
+        counter["i"] = i + 1
+        return r
+
+    _lib.lasso_lars = timed_lars
+    barrier()
+    ev0.record(main)
+    for _ in range(K):
+        t += 1
+        one_step(t)
+    eng.flush()
+    ev1.record(main)
+    barrier()
+    _lib.lasso_lars = orig_lars
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    lars_ms = float(np.mean([a.elapsed_time(b) for a, b in lars_ev]))
+    launches = (eng.launches - launches0) + K          # + the gather kernel per step
+    stats = eng.read_stats()
+    tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(tmax.item())
+    value = n_global * K / (elapsed_ms * 1e-3)
+
+    # ---------------- end-to-end: pinned host minibatches through OnmfEngine.step_host -----------------------
+    host = [torch.empty(n, d, dtype=dt).pin_memory() for _ in range(2)]
+    for hbuf in host:
+        hbuf.copy_(pool)                                   # synthetic host-resident minibatches
+    W_host = torch.empty(d, k, dtype=dt).pin_memory()
+    e2e_steps = max(3, min(K, 8))
+    for i in range(2):
+        t += 1
+        eng.step_host(host[i & 1], float(t), W_host)
+    eng.flush()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for i in range(e2e_steps):
+        t += 1
+        eng.step_host(host[i & 1], float(t), W_host)
+    eng.flush()
+    e1.record(main)
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = n_global * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+    checksum = float(W_host.double().sum())
+    assert np.isfinite(checksum)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel (LARS coder) -------------------------------------------
+    hbm_peak, peak_src = measured_peaks()
+    tsz = 4
+    alg_bytes = (2.0 * n * k + k * k) * tsz                 # read Ct (n x k) + G (k x k), write Ht (n x k), once
+    achieved = alg_bytes / (lars_ms * 1e-3) / 1e9
+    cols = max(stats["columns"] + stats["overflow"], 1)
+    # executed work of the solver, counted in-kernel: per knot with active size s the kernel does one k x s
+    # correlation pass (2ks flop) and ~9 s^2 flop of inverse-update / refinement passes
+    flop = 2.0 * k * stats["sum_active"] + 9.0 * stats["sum_active2"]
+    smem_bytes = (1.0 * k * stats["sum_active"] + 5.0 * stats["sum_active2"]) * tsz
+    lars_total_s = lars_ms * 1e-3 * K
+    sm_clock = (clocks.get("sm_mhz") or 1900.0) * 1e6
+    fp32_peak = 148 * 128 * 2 * sm_clock / 1e12               # TFLOP/s at the observed clock
+    smem_peak = 148 * 128 * sm_clock / 1e9                    # GB/s  (128 B/clk/SM)
+    roofline = {"bound": "hbm", "kernel": "lars_kernel (K3 sparse coder)", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": lars_ms, "share_of_step": lars_ms * K / elapsed_ms,
+                "note": "the coder is FP32-FMA / shared-memory bound, not HBM bound; see lars_work"}
+    lars_work = {"knots_per_column": stats["knots"] / cols, "mean_active": stats["sum_active"] / max(stats["knots"], 1),
+                 "max_active": stats["max_active"], "drops_per_column": stats["drops"] / cols,
+                 "overflow_columns": stats["overflow"], "flagged_columns": stats["flagged"],
+                 "executed_gflop_per_step": flop / K / 1e9, "fp32_tflops_achieved": flop / lars_total_s / 1e12,
+                 "fp32_tflops_peak_at_clock": fp32_peak, "fp32_frac": flop / lars_total_s / 1e12 / fp32_peak,
+                 "smem_gbs_achieved": smem_bytes / lars_total_s / 1e9, "smem_gbs_peak_at_clock": smem_peak,
+                 "smem_frac": smem_bytes / lars_total_s / 1e9 / smem_peak}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ccols = args.cpu_cols or {"cfg5": 1536, "cfg4": 4096, "cfg3": 8192, "cfg2": 4000, "cfg1": 1000}[args.workload]
+        cval, csec = cpu_reference_step(d, k, alpha, ccols, steps=1, warmup=0)
+        cpu = {"value": cval, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d of %d columns, 1 step (%.1f s), numpy + scikit-learn lasso_lars via the oracle port; "
+                         "per-sample LARS loop single-threaded, host cpus=%s" % (ccols, n_global, csec, os.cpu_count())}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: synthetic U[0,1) d=%d k=%d global minibatch %d (%d columns/GPU) alpha=%g; "
+                               "fresh minibatch per step resampled from a resident pool; inputs (%.2f GB/GPU) larger than L2"
+                               % (args.workload, d, k, n_global, n, alpha, n * d * 4 / 1e9),
+                   "d": d, "k": k, "global_batch": n_global, "parallelism": "dp%d (column shards, all-reduce of k x (k+d))" % world},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": d * k * 4,
+                "steps": e2e_steps, "api": "OnmfEngine.step_host(pinned Xt, t, W_out_host)"},
+        "roofline": roofline, "lars_work": lars_work, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-cols", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: relaunch under torchrun on one node
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -171,6 +171,38 @@ class OnmfEngine:
         self._cur ^= 1
         return Ht
 
+    # ------------------------------------------------------------------ host-buffer entry (end-to-end path)
+    def step_host(self, Xt_host: torch.Tensor, t: float, W_out_host: Optional[torch.Tensor] = None):
+        """step() for a minibatch that lives in (pinned) HOST memory, sample-major (n x d).
+
+        The host->device copy runs on a copy stream into one of two staging buffers, so the copy of
+        minibatch t+1 overlaps the coding of minibatch t; if W_out_host (pinned, d x k) is given the updated
+        dictionary is copied back asynchronously after the step's dictionary update.  Nothing blocks the host;
+        call flush()+synchronize (or read_back()) before touching W_out_host."""
+        if Xt_host.is_cuda:
+            raise _lib.OnmfKernelError("step_host expects a host tensor")
+        n = Xt_host.shape[0]
+        if not hasattr(self, "_stage") or self._stage[0].shape[0] < n:
+            self._stage = [torch.empty(max(n, 1), self.d, dtype=self.dtype, device=self.device) for _ in range(2)]
+            self._stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_i = 0
+            self._copy = torch.cuda.Stream(self.device)
+            self._ev_h2d = torch.cuda.Event()
+        i = self._stage_i
+        self._stage_i ^= 1
+        buf = self._stage[i][:n]
+        with torch.cuda.stream(self._copy):
+            self._copy.wait_event(self._stage_ev[i])       # the step that last used this buffer is done with it
+            buf.copy_(Xt_host, non_blocking=True)
+            self._ev_h2d.record(self._copy)
+        self.main.wait_event(self._ev_h2d)
+        Ht = self.step(buf, t)
+        self._stage_ev[i].record(self.main)
+        if W_out_host is not None:
+            with torch.cuda.stream(self.side):
+                W_out_host.copy_(self.W, non_blocking=True)     # self.W is the dictionary this step produced
+        return Ht
+
     def flush(self):
         """Make W, A, B (C) visible to the current stream / host."""
         self.main.wait_stream(self.side)

@@ -1,0 +1,333 @@
+"""Parity of the CUDA path (through the C ABI / the reference-facing classes) against the oracle and the
+reference's golden fixtures.  Tolerances (BASELINE.json north_star):
+  fp64 mode : per-minibatch codes within 1e-4 relative L2 of the reference lasso_lars codes
+              (measured ~1e-11; asserted at 1e-8 to catch regressions)
+  fp32 mode : final dictionary per atom within 1e-3; reconstruction error within 0.5 %.
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from onmf_ontf_ndl_b200 import Online_NMF, Online_NTF, OnmfEngine, _lib, update_code_within_radius
+from oracle import c_oracle
+from oracle import onmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings("ignore")
+
+CASES = ["cfg1_renoir_gray", "cfg1_alpha0", "cfg2_renoir_color_tensor", "cfg3_binary_motif", "cfg4_ising_pm1"]
+CODE_TOL_FP64 = 1e-8       # north_star bar: 1e-4
+CODE_TOL_FP32 = 2e-3       # per-minibatch fp32 codes (not a north_star bar; W / recon bars below are)
+ATOM_TOL_FP32 = 1e-3       # north_star
+RECON_TOL = 5e-3           # north_star: reconstruction error within 0.5 %
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def per_atom(W, Wref):
+    return float(np.max(np.linalg.norm(W - Wref, axis=0) / np.maximum(np.linalg.norm(Wref, axis=0), 1e-30)))
+
+
+def tt(x, dt):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev(), dt)
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def test_extension_is_the_native_library():
+    lib = _lib.load()
+    assert lib.onmf_built_arch() == 100
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+# ---------------------------------------------------------------------------------------------- K2 / K4
+@pytest.mark.parametrize("dt,tol", [(torch.float64, 1e-13), (torch.float32, 2e-6)])
+@pytest.mark.parametrize("n,d,k", [(300, 100, 25), (257, 300, 49), (1000, 441, 25), (513, 400, 100), (640, 1024, 256), (1, 7, 3)])
+def test_gram_cov_surrogate(dt, tol, n, d, k):
+    rng = np.random.default_rng(n + d + k)
+    X, W = rng.random((n, d)), rng.random((d, k))
+    H = rng.random((n, k)) * (rng.random((n, k)) < 0.2)
+    Xt, Wd, Ht = tt(X, dt), tt(W, dt), tt(H, dt)
+    G = torch.empty(k, k, dtype=dt, device=dev())
+    Ct = torch.empty(n, k, dtype=dt, device=dev())
+    P = torch.empty(k, k + d, dtype=dt, device=dev())
+    ws = torch.empty(_lib.surrogate_workspace(dt, n, k, d), dtype=torch.uint8, device=dev())
+    _lib.gram(Wd, G); _lib.cov(Xt, Wd, Ct); _lib.surrogate_partial(Ht, Xt, P, ws)
+    Pn = P.cpu().numpy()
+    assert rel(G.cpu().numpy(), W.T @ W) < tol and rel(Ct.cpu().numpy(), X @ W) < tol
+    assert rel(Pn[:, :k], H.T @ H) < tol and rel(Pn[:, k:], H.T @ X) < tol
+    A, B = rng.random((k, k)), rng.random((k, d))
+    Ad, Bd = tt(A, dt), tt(B, dt)
+    _lib.surrogate_blend(P, 0.25, Ad, Bd)
+    Aref, Bref = O.aggregate(A, B, H.T, X.T, 4.0)
+    assert rel(Ad.cpu().numpy(), Aref) < tol and rel(Bd.cpu().numpy(), Bref) < tol
+
+
+def test_surrogate_is_deterministic_and_symmetric():
+    rng = np.random.default_rng(0)
+    n, d, k = 5000, 100, 25
+    Ht = tt(rng.random((n, k)), torch.float32); Xt = tt(rng.random((n, d)), torch.float32)
+    ws = torch.empty(_lib.surrogate_workspace(torch.float32, n, k, d), dtype=torch.uint8, device=dev())
+    P1 = torch.empty(k, k + d, dtype=torch.float32, device=dev()); P2 = torch.empty_like(P1)
+    _lib.surrogate_partial(Ht, Xt, P1, ws); _lib.surrogate_partial(Ht, Xt, P2, ws)
+    assert torch.equal(P1, P2)                               # fixed-order split-K reduction
+    assert torch.equal(P1[:, :k], P1[:, :k].T.contiguous())  # HtH bitwise symmetric
+
+
+# ---------------------------------------------------------------------------------------------- K5
+# fp32 tolerance: the sweep subtracts two O(100) numbers (W A[:,j] and B[j,:]) to get an O(0.01) update, so
+# fp32 rounding is amplified ~1e4x on these synthetic magnitudes (measured 2e-4 at d=2700); fp64 pins the logic.
+@pytest.mark.parametrize("dt,tol", [(torch.float64, 1e-12), (torch.float32, 1e-3)])
+@pytest.mark.parametrize("d,k", [(100, 25), (300, 49), (441, 25), (400, 100), (1024, 256), (2700, 25), (77, 3), (5, 1)])
+def test_update_dict(dt, tol, d, k):
+    rng = np.random.default_rng(d * k)
+    W = rng.random((d, k)); H = rng.random((k, 200))
+    A, B = H @ H.T / 7, H @ rng.random((200, d)) / 7
+    Wd, out = tt(W, dt), torch.empty(d, k, dtype=dt, device=dev())
+    _lib.update_dict(Wd, tt(A, dt), tt(B, dt), out)
+    ref = O.update_dict(W, A, B)
+    got = out.cpu().numpy().astype(np.float64)
+    assert per_atom(got, ref) < tol
+    assert got.min() >= 0 and np.all(np.linalg.norm(got, axis=0) <= 1 + 1e-6)
+    _lib.update_dict(Wd, tt(A, dt), tt(B, dt), Wd)                     # in place
+    assert torch.equal(Wd, out)
+    # zero aggregates: clamp + shrink only (first step of every run)
+    z = torch.empty_like(out)
+    _lib.update_dict(tt(W, dt), torch.zeros(k, k, dtype=dt, device=dev()), torch.zeros(k, d, dtype=dt, device=dev()), z)
+    assert rel(z.cpu().numpy(), W / np.maximum(1.0, np.linalg.norm(W, axis=0))) < tol
+
+
+# ---------------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("name", CASES)
+def test_codes_vs_reference_golden_every_step(golden_dir, name):
+    g = load(golden_dir, name)
+    alpha = float(g["alpha"])
+    for i in range(int(g["n_steps"])):
+        W = g["W0"] if i == 0 else g["W_%d" % (i - 1)]
+        Xb = g["X"][:, g["idx"][i]]
+        Href = g["H_%d" % i]
+        eng = OnmfEngine(W.shape[0], W.shape[1], alpha=alpha, dtype=torch.float64, device=dev(), collect_stats=True)
+        H = eng.sparse_code(tt(Xb.T, torch.float64), tt(W, torch.float64)).cpu().numpy().T
+        assert rel(H, Href) < CODE_TOL_FP64, (name, i)
+        st = eng.read_stats()
+        assert st["columns"] == Xb.shape[1] and st["flagged"] == 0
+        if not (alpha == 0.0 and i > 0):          # alpha=0 on an ill-conditioned learned dictionary: NNLS is fp32-sensitive
+            eng32 = OnmfEngine(W.shape[0], W.shape[1], alpha=alpha, dtype=torch.float32, device=dev())
+            H32 = eng32.sparse_code(tt(Xb.T, torch.float32), tt(W, torch.float32)).cpu().numpy().T
+            assert rel(H32, Href) < CODE_TOL_FP32, (name, i)
+
+
+def test_codes_cfg5_and_overflow_path(golden_dir):
+    """d=1024, k=256 on the raw U[0,1) W0: active sets exceed the 64-slot fast path -> exercises the large path."""
+    g = load(golden_dir, "cfg5_synthetic")
+    X = np.random.RandomState(int(g["x_seed"])).rand(1024, 160)
+    W0 = np.random.RandomState(int(g["w0_seed"])).rand(1024, 256)
+    Xb = X[:, g["idx"][0]]
+    for dt, tol in ((torch.float64, CODE_TOL_FP64), (torch.float32, CODE_TOL_FP32)):
+        eng = OnmfEngine(1024, 256, alpha=1.0, dtype=dt, device=dev(), collect_stats=True)
+        H = eng.sparse_code(tt(Xb.T, dt), tt(W0, dt)).cpu().numpy().T
+        assert rel(H, g["H_0"]) < tol
+        st = eng.read_stats()
+        assert st["overflow"] > 0 and st["max_active"] > 64 and st["columns"] == Xb.shape[1]
+
+
+@pytest.mark.parametrize("d,k,n,alpha", [(64, 20, 333, 1.0), (64, 20, 64, 0.0), (50, 33, 100, 0.3), (120, 70, 90, 1.0),
+                                          (200, 130, 60, 0.5), (30, 7, 1, 1.0), (16, 3, 5, 2.0)])
+def test_codes_vs_c_oracle_fresh_inputs(d, k, n, alpha):
+    rng = np.random.default_rng(d + k + n)
+    W = rng.random((d, k)); W /= np.linalg.norm(W, axis=0)
+    X = rng.random((d, n))
+    if n > 3:
+        X[:, 2] = 0.0                       # empty sample
+        X[:, 3] = -X[:, 3]                  # all covariances negative -> never activates
+    Href = c_oracle.sparse_code(X, W, alpha)
+    eng = OnmfEngine(d, k, alpha=alpha, dtype=torch.float64, device=dev())
+    H = eng.sparse_code(tt(X.T, torch.float64), tt(W, torch.float64)).cpu().numpy().T
+    assert rel(H, Href) < CODE_TOL_FP64
+    if n > 3:
+        assert np.all(H[:, 2] == 0) and np.all(H[:, 3] == 0)
+    assert H.min() >= -1e-12
+
+
+def test_codes_satisfy_kkt_at_scale():
+    """size-independent property at a bench-like shape: nonnegativity and lasso KKT conditions
+    (G h - c + alpha >= 0 off the support up to the LARS last-segment shift, |.| small on the support)."""
+    d, k, n, alpha = 1024, 256, 8192, 1.0
+    g = torch.Generator(device=dev()); g.manual_seed(0)
+    Xt = torch.rand(n, d, dtype=torch.float32, device=dev(), generator=g)
+    W = torch.rand(d, k, dtype=torch.float32, device=dev(), generator=g)
+    W = W / W.norm(dim=0, keepdim=True)
+    eng = OnmfEngine(d, k, alpha=alpha, dtype=torch.float32, device=dev(), collect_stats=True)
+    Ht = eng.sparse_code(Xt, W).clone()
+    assert float(Ht.min()) >= 0.0
+    G = (W.double().T @ W.double()); C = Xt.double() @ W.double()
+    grad = Ht.double() @ G - C + alpha                          # n x k
+    on = Ht > 0
+    assert float(grad[on].abs().max()) < 0.05                    # alpha_eff in [0.9993, 1.0202]*alpha
+    assert float(grad[~on].min()) > -0.05
+    st = eng.read_stats()
+    assert st["columns"] == n and st["flagged"] <= n // 1000
+
+
+# ---------------------------------------------------------------------------------------------- whole path
+@pytest.mark.parametrize("name", ["cfg1_renoir_gray", "cfg3_binary_motif", "cfg4_ising_pm1", "cfg2_renoir_color_tensor"])
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_online_ntf_train_matches_reference(golden_dir, name, precision):
+    """Online_NTF.train_dict_single under the reference's seed: same W0 / minibatch order (host RNG replay)."""
+    g = load(golden_dir, name)
+    seeds = {"cfg1_renoir_gray": 11, "cfg2_renoir_color_tensor": 21, "cfg3_binary_motif": 31, "cfg4_ising_pm1": 41}
+    ns = int(g["n_steps"])
+    k = g["W0"].shape[1]
+    batch = g["idx"].shape[1]
+    if name == "cfg2_renoir_color_tensor":
+        X3, mode, joint = g["T"], 2, True
+    else:
+        X3, mode, joint = g["X"][:, :, None], 0, False
+    np.random.seed(seeds[name])
+    m = Online_NTF(X3, n_components=k, iterations=ns + 1, batch_size=batch, alpha=float(g["alpha"]), mode=mode,
+                   learn_joint_dict=joint, precision=precision)
+    W, A, B, code = m.train_dict_single()
+    assert W.dtype == np.float64 and W.shape == g["W_final"].shape and code.shape == (X3.shape[1], k)
+    assert float(m.history) == float(g["history_out"])
+    if precision == "fp64":
+        assert per_atom(W, g["W_final"]) < 1e-8 and rel(A, g["A_final"]) < 1e-8 and rel(B, g["B_final"]) < 1e-8
+    else:
+        assert per_atom(W, g["W_final"]) < ATOM_TOL_FP32
+        assert rel(A, g["A_final"]) < 5e-3 and rel(B, g["B_final"]) < 5e-3
+        # reconstruction error with reference codes for both dictionaries
+        Xe = g["X"][:, :80]
+        e_ref = np.linalg.norm(Xe - g["W_final"] @ O.sparse_code_sklearn(Xe, g["W_final"], float(g["alpha"]))) / np.linalg.norm(Xe)
+        e_got = np.linalg.norm(Xe - W @ O.sparse_code_sklearn(Xe, W, float(g["alpha"]))) / np.linalg.norm(Xe)
+        assert abs(e_got - e_ref) <= RECON_TOL * e_ref
+
+
+def test_chained_epochs_alphaNone_beta(golden_dir):
+    g2 = load(golden_dir, "cfg1_renoir_gray_epoch2")
+    np.random.seed(12)
+    m = Online_NTF(g2["X"][:, :, None], n_components=25, iterations=int(g2["n_steps"]) + 1, batch_size=g2["idx"].shape[1],
+                   ini_dict=g2["W0"], ini_A=g2["A0"], ini_B=g2["B0"], history=float(g2["history_in"]), alpha=1,
+                   precision="fp64")
+    W, A, B, _ = m.train_dict_single()
+    assert per_atom(W, g2["W_final"]) < 1e-8 and rel(A, g2["A_final"]) < 1e-8
+    assert float(m.history) == float(g2["history_out"])
+    g3 = load(golden_dir, "cfg1_alphaNone_beta_full")       # alpha=None -> 2, beta=0.75, subsample=False
+    np.random.seed(13)
+    m = Online_NTF(g3["X"][:, :, None], n_components=25, iterations=int(g3["n_steps"]) + 1, batch_size=200, alpha=None,
+                   beta=0.75, subsample=False, precision="fp64")
+    W, A, B, _ = m.train_dict_single()
+    assert per_atom(W, g3["W_final"]) < 1e-8 and rel(A, g3["A_final"]) < 1e-8 and rel(B, g3["B_final"]) < 1e-8
+
+
+def test_step_and_coder_methods(golden_dir):
+    g = load(golden_dir, "cfg4_ising_pm1")
+    i = 2
+    W, A, B = g["W_%d" % (i - 1)], g["A_%d" % (i - 1)], g["B_%d" % (i - 1)]
+    Xb = g["X"][:, g["idx"][i]]
+    m = Online_NTF(g["X"][:, :, None], n_components=100, alpha=1, precision="fp64")
+    H1, A1, B1, W1 = m.step(Xb, A, B, W, np.float64(i + 1))
+    assert H1.shape == (Xb.shape[1], 100)                            # n x r like the reference
+    assert rel(H1.T, g["H_%d" % i]) < 1e-8 and rel(A1, g["A_%d" % i]) < 1e-8 and rel(B1, g["B_%d" % i]) < 1e-8
+    assert per_atom(W1, g["W_%d" % i]) < 1e-8 and float(m.history) == i + 2
+    assert rel(m.joint_sparse_code_tensor(Xb, W).T, g["H_%d" % i]) < 1e-8
+    assert per_atom(m.update_dict(W, A, B), g["W_%d" % i]) < 1e-8
+    # Online_NMF: same arithmetic, r x n codes, driver-style 5-tuple
+    nm = Online_NMF(g["X"], n_components=100, alpha=1, precision="fp64")
+    assert rel(nm.sparse_code(Xb, W), g["H_%d" % i]) < 1e-8
+    H2, agg, W2 = nm.step(Xb, [A, B], W, np.float64(i + 1))
+    assert rel(H2, g["H_%d" % i]) < 1e-8 and rel(agg[0], g["A_%d" % i]) < 1e-8 and per_atom(W2, g["W_%d" % i]) < 1e-8
+
+
+def test_online_nmf_train_dict_driver_style(golden_dir):
+    """Online_NMF.train_dict (lasso coder, accumulating aggregates, subsample=True) == oracle loop; 5-tuple with Ct."""
+    g = load(golden_dir, "cfg1_renoir_gray")
+    X = g["X"][:, :400]
+    np.random.seed(5)
+    m = Online_NMF(X, n_components=25, iterations=4, batch_size=100, alpha=1, subsample=True, precision="fp64")
+    W, At, Bt, Ct, H = m.train_dict()
+    rs = np.random.RandomState(5)
+    W0 = rs.rand(100, 25)
+    idx = [rs.randint(400, size=100) for _ in range(3)]
+    Wr, Ar, Br = W0, np.zeros((25, 25)), np.zeros((25, 100))
+    Cr = np.zeros((100, 100)); code = np.zeros((25, 400))
+    for i, ii in enumerate(idx, start=1):
+        Hh, A1, B1, W1 = c_oracle.step(X[:, ii], Ar, Br, Wr, float(i), 1.0)
+        Cr = (1 - 1.0 / i) * Cr + (1.0 / i) * X[:, ii] @ X[:, ii].T
+        code[:, ii] += Hh
+        Wr, Ar, Br = W1, A1, B1
+    assert per_atom(W, Wr) < 1e-8 and rel(At, Ar) < 1e-8 and rel(Bt, Br) < 1e-8 and rel(Ct, Cr) < 1e-10
+    assert rel(H, code) < 1e-8 and float(m.history) == 4.0
+    err = O.surrogate_error(W, At, Bt, Ct)                      # ising_reconstruction.py:133 readout works
+    assert np.isfinite(err)
+
+
+def test_pgd_coder_and_shipped_compat(golden_dir):
+    g = load(golden_dir, "pgd_coder")
+    H = update_code_within_radius(g["X"], g["W"], H0=g["H0"], r=None, alpha=1, sub_iter=10, stopping_diff=0.01,
+                                  precision="fp64")
+    assert rel(H, g["H"]) < 1e-9
+    H1 = update_code_within_radius(g["X"][:, :1], g["W"], H0=g["H0"][:, :1], r=None, alpha=1, sub_iter=10,
+                                   stopping_diff=0.01, precision="fp64")
+    assert rel(H1, g["H_single"]) < 1e-9
+    with pytest.raises(NotImplementedError):
+        update_code_within_radius(g["X"], g["W"], H0=g["H0"], r=0.5)
+    s = load(golden_dir, "shipped_onmf")                     # literal shipped src/onmf.py run, seed 71
+    np.random.seed(int(s["seed"]))
+    m = Online_NMF(s["X"], n_components=25, iterations=4, batch_size=60, alpha=1, subsample=True, compat="shipped_onmf",
+                   precision="fp64")
+    W, agg, code = m.train_dict()
+    assert per_atom(W, s["W"]) < 1e-8 and rel(agg[0], s["A"]) < 1e-8 and rel(agg[1], s["B"]) < 1e-8
+    assert rel(code, s["code"]) < 1e-8 and float(m.history) == float(s["history_out"])
+
+
+# ---------------------------------------------------------------------------------------------- K1
+def test_gathers(golden_dir):
+    g = load(golden_dir, "cfg1_renoir_gray")
+    for dt in (torch.float64, torch.float32):
+        img = tt(g["img"], dt); co = torch.from_numpy(g["coords"].astype(np.int32)).to(dev())
+        out = torch.empty(co.shape[0], 100, dtype=dt, device=dev())
+        _lib.gather_patches(img, co, 10, out)
+        assert np.array_equal(out.cpu().numpy().T, g["X"].astype(out.cpu().numpy().dtype))
+    g2 = load(golden_dir, "cfg2_renoir_color_tensor")
+    img = tt(g2["img"], torch.float64); co = torch.from_numpy(g2["coords"].astype(np.int32)).to(dev())
+    out = torch.empty(co.shape[0], 300, dtype=torch.float64, device=dev())
+    _lib.gather_patches(img, co, 10, out)
+    assert np.array_equal(out.cpu().numpy().T, g2["X"])              # HWC feature order == mode-2 joint unfolding
+    g4 = load(golden_dir, "cfg4_ising_pm1")
+    img = tt(g4["img"], torch.float32); co = torch.from_numpy(g4["coords"].astype(np.int32)).to(dev())
+    out = torch.empty(co.shape[0], 400, dtype=torch.float32, device=dev())
+    _lib.gather_patches(img, co, 20, out)
+    assert np.array_equal(out.cpu().numpy().T.astype(np.float64), g4["X"])
+    pool = tt(g["X"].T, torch.float64); idx = torch.from_numpy(g["idx"][0].astype(np.int64)).to(dev())
+    xb = torch.empty(len(idx), 100, dtype=torch.float64, device=dev())
+    _lib.gather_rows(pool, idx, xb)
+    assert np.array_equal(xb.cpu().numpy().T, g["X"][:, g["idx"][0]])
+    src = tt(np.arange(35 * 77, dtype=np.float64).reshape(35, 77), torch.float64)
+    dst = torch.empty(77, 35, dtype=torch.float32, device=dev())
+    _lib.transpose(src, dst)
+    assert torch.equal(dst, src.T.to(torch.float32))
+    # empty inputs are no-ops
+    _lib.gather_rows(pool, idx[:0], xb[:0])
+
+
+def test_empty_minibatch_and_loud_failures():
+    eng = OnmfEngine(20, 5, alpha=1.0, dtype=torch.float32, device=dev())
+    W0 = torch.rand(20, 5, device=dev())
+    eng.set_state(W0.cpu().numpy())
+    eng.step(torch.empty(0, 20, device=dev()), 1.0)                 # a rank may own zero columns
+    W, A, B, _ = eng.state()
+    assert float(A.abs().max()) == 0.0
+    with pytest.raises(_lib.OnmfKernelError):
+        _lib.gram(torch.rand(4, 3), torch.empty(3, 3))               # CPU tensors are refused, not silently handled
+    with pytest.raises(_lib.OnmfKernelError):
+        OnmfEngine(10, 600, device=dev()).sparse_code(torch.rand(4, 10, device=dev()))   # k > 512 unsupported
