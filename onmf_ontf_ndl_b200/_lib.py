@@ -118,6 +118,8 @@ def gather_patches(img, coords, p, out, stream=None):
 
 def gather_rows(pool, idx, out, stream=None):
     _req(pool, "pool"); _req(idx, "idx", torch.int64); _req(out, "out", pool.dtype)
+    if idx.shape[0] == 0:
+        return out
     _check(load().onmf_gather_rows(dt(pool), _ptr(pool), pool.shape[0], pool.shape[1], _ptr(idx), idx.shape[0],
                                    _ptr(out), _stream(stream)), "onmf_gather_rows")
     return out

@@ -7,23 +7,30 @@
 //
 // Mapping: one lane-group (LPC = 8/16/32 lanes) follows the homotopy path of one minibatch column; a
 // warp carries 32/LPC columns, a CTA carries NW warps, columns are handed out through a global ticket
-// counter.  The Gram matrix G = W^T W is staged once per CTA in shared memory (when it fits); each
-// group keeps the inverse of the active Gram block, M = G_AA^-1, in its own shared-memory tile and
-// maintains it by bordering (atom joins) / Schur downdate (atom leaves).  That replaces sklearn's
-// Cholesky factor + two triangular solves per knot (3 s dependent steps) by two s x s lane-parallel
-// passes; in fp32 one step of iterative refinement on the equiangular weights restores the accuracy
-// (measured: 2.6e-5 rel. code error on a cond(G)=1.5e5 learned dictionary versus 1.2e-3 without).
-// All lane<->lane traffic is warp shuffles; the only barriers are __syncwarp().
+// counter.  The Gram matrix G = W^T W is staged once per CTA in shared memory when it fits (k <= 128 in
+// fp32), otherwise read through L1/L2 with the row loads of a pass batched four rows deep.  Each group
+// keeps the inverse of its active Gram block, M = G_AA^-1, packed lower-triangular in FP64 in its own
+// shared-memory tile and maintains it by bordering (atom joins) / Schur downdate (atom leaves): two
+// lane-parallel s x s passes per knot instead of sklearn's Cholesky append + two triangular solves
+// (3 s dependent steps).  M is FP64 also in the fp32 production mode: on the ill-conditioned dictionaries
+// of the first online steps (cond(G) ~ 4e5) an fp32 inverse costs 3e-3 relative code error, the fp64
+// inverse 9e-5, for ~20 % more shared-memory traffic (measured).  Covariances, correlations,
+// step lengths and coefficients are in the working precision T.  Cross-lane reductions are single REDUX
+// instructions on order-preserving integer keys (fp32) or shuffle trees (fp64 / sums); the only barriers
+// are __syncwarp().
 //
 // Path semantics reproduced from sklearn (so the result matches the reference also where sklearn is
 // not at the exact lasso optimum):
 //   - join: inactive atom with the largest covariance (ties: lowest index)
 //   - recorded alpha of a knot = max INACTIVE covariance / d; stop when alpha <= alpha/d + eps32 and
-//     interpolate linearly between the last two coefficient vectors
+//     interpolate linearly between the last two coefficient vectors (incl. the atom dropped by the last
+//     step, which is still positive inside that segment)
 //   - step gamma = min(min_pos((C-c_i)/(AA-a_i+tiny32)), C/AA); drop when a coefficient would cross 0
 //     first (gamma = z_pos), no atom joins on the iteration after a drop, the dropped atom's covariance
 //     is recomputed exactly
 //   - "alpha increasing" bail-out, degenerate-pivot rejection (cov := 0), max_iter.
+// Columns whose active set outgrows a tier's slot count are queued (device-side list) for the next tier:
+// tier 0 = 64 slots (32 for k <= 32), tier 1 = 128 slots in shared memory, tier 2 = k slots with M in global.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -33,18 +40,20 @@ namespace onmf {
 template <typename T>
 struct LarsParams {
   const T* G;        // k x k
+  const T* Gp;       // k x KP zero-padded copy (workspace)
   const T* Ct;       // n x k
   T* Ht;             // n x k
   long long n;
   int k, d, max_iter;
   T amin;            // alpha / d
   unsigned long long* ticket;        // work counter (zeroed by the host wrapper)
-  const long long* col_list;         // overflow pass: columns to solve (else nullptr)
-  const unsigned int* n_list;        // overflow pass: device-side count
-  long long* ovf_list;               // main pass: columns whose active set outgrew SMAX
+  const long long* col_list;         // later tiers: columns to solve (else nullptr)
+  const unsigned int* n_list;        // later tiers: device-side count
+  long long* ovf_list;               // columns whose active set outgrew this tier
   unsigned int* ovf_count;
-  T* Mscratch;                       // overflow pass: per-group M storage in global memory
+  double* Mscratch;                  // last tier: per-group M storage in global memory
   onmf_lars_stats* stats;
+  int count_stats;                   // 1 on the first tier (overflow columns are counted once)
 };
 
 template <typename T> struct Num;
@@ -57,48 +66,112 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double big() { return 1.7976931348623157e+308; }
 };
 
-template <typename T, int LPC>
-__device__ __forceinline__ T gsum(T v) {
+// ---- group reductions ------------------------------------------------------------------------------
+template <int LPC>
+__device__ __forceinline__ double gsum(double v) {
 #pragma unroll
   for (int off = LPC / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
   return v;
 }
-template <typename T, int LPC>
-__device__ __forceinline__ T gmin(T v) {
+template <int LPC>
+__device__ __forceinline__ float gsum(float v) {
+#pragma unroll
+  for (int off = LPC / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+__device__ __forceinline__ unsigned fkey(float f) {     // order-preserving float -> uint
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// (max value, lowest index attaining it)
+template <int LPC>
+__device__ __forceinline__ void gargmax(float& v, int& i, unsigned gmask) {
+  unsigned key = fkey(v);
+  unsigned kmax = __reduce_max_sync(gmask, key);
+  int cand = (key == kmax) ? i : 0x7fffffff;
+  i = __reduce_min_sync(gmask, cand);
+  v = fkey_inv(kmax);
+}
+template <int LPC>
+__device__ __forceinline__ void gargmax(double& v, int& i, unsigned) {
 #pragma unroll
   for (int off = LPC / 2; off > 0; off >>= 1) {
-    T o = __shfl_xor_sync(0xffffffffu, v, off);
+    double ov = __shfl_xor_sync(0xffffffffu, v, off);
+    int oi = __shfl_xor_sync(0xffffffffu, i, off);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+// min over strictly positive candidates (callers pass big() for "none")
+template <int LPC>
+__device__ __forceinline__ float gminpos(float v, unsigned gmask) {
+  return __uint_as_float(__reduce_min_sync(gmask, __float_as_uint(v)));
+}
+template <int LPC>
+__device__ __forceinline__ double gminpos(double v, unsigned) {
+#pragma unroll
+  for (int off = LPC / 2; off > 0; off >>= 1) {
+    double o = __shfl_xor_sync(0xffffffffu, v, off);
     v = o < v ? o : v;
   }
   return v;
 }
+// (min positive value, highest slot attaining it)
 template <int LPC>
-__device__ __forceinline__ int gmini(int v) {
-#pragma unroll
-  for (int off = LPC / 2; off > 0; off >>= 1) {
-    int o = __shfl_xor_sync(0xffffffffu, v, off);
-    v = o < v ? o : v;
-  }
-  return v;
+__device__ __forceinline__ void gargminpos(float& v, int& s, unsigned gmask) {
+  unsigned key = __float_as_uint(v);
+  unsigned kmin = __reduce_min_sync(gmask, key);
+  int cand = (key == kmin) ? s : -1;
+  s = __reduce_max_sync(gmask, cand);
+  v = __uint_as_float(kmin);
 }
 template <int LPC>
-__device__ __forceinline__ int gmaxi(int v) {
+__device__ __forceinline__ void gargminpos(double& v, int& s, unsigned) {
 #pragma unroll
   for (int off = LPC / 2; off > 0; off >>= 1) {
-    int o = __shfl_xor_sync(0xffffffffu, v, off);
-    v = o > v ? o : v;
+    double ov = __shfl_xor_sync(0xffffffffu, v, off);
+    int os = __shfl_xor_sync(0xffffffffu, s, off);
+    if (ov < v || (ov == v && os > s)) { v = ov; s = os; }
   }
-  return v;
 }
 
-// shared-memory words (4 B) one group needs, padded so that consecutive groups of a warp start LPC banks apart
+// ---- fast FP64 reciprocal / reciprocal square root: fp32 seed + two Newton steps (rel. error < 1e-14) ----
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y = (double)__frcp_rn((float)x);
+  y = y * (2.0 - x * y);
+  y = y * (2.0 - x * y);
+  return y;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y = (double)rsqrtf((float)x);
+  y = y * (1.5 - 0.5 * x * y * y);
+  y = y * (1.5 - 0.5 * x * y * y);
+  return y;
+}
+__device__ __forceinline__ float qdiv(float a, float b) { return __fdividef(a, b); }   // step-length candidates
+__device__ __forceinline__ double qdiv(double a, double b) { return a / b; }
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { typedef float4 type; static constexpr int N = 4; };
+template <> struct VecOf<double> { typedef double2 type; static constexpr int N = 2; };
+
+// slot entry read by the correlation pass: (atom, normalised weight); free slots hold (0, 0)
+template <typename T> struct SlotW;
+template <> struct __align__(8) SlotW<float> { int atom; float w; };
+template <> struct __align__(16) SlotW<double> { int atom; int pad; double w; };
+
+// shared-memory words (4 B) one group needs: FP64 M (packed lower triangle above 32 slots, full square up to 32;
+// absent when M lives in global), g/u (FP64), slot entries, slot->atom
 template <typename T, int LPC, int SMAX, bool MGLOB>
 __host__ __device__ constexpr int group_words() {
-  int tw = sizeof(T) / 4;
-  int w = (MGLOB ? 0 : SMAX * SMAX * tw) + 3 * SMAX * tw + SMAX;
-  if (LPC < 32) {
+  int mwords = (SMAX > 32) ? SMAX * (SMAX + 1) : 2 * SMAX * SMAX;
+  int w = (MGLOB ? 0 : mwords) + 4 * SMAX + SMAX * (int)(sizeof(SlotW<T>) / 4) + SMAX;
+  w = (w + 3) & ~3;                       // keep 16-byte alignment of the next group
+  if (LPC < 32) {                         // start consecutive groups of a warp 2*LPC banks apart
     int r = w % 32;
-    int want = LPC % 32;
+    int want = (2 * LPC) % 32;
     w += (want - r + 32) % 32;
   }
   return w;
@@ -108,13 +181,27 @@ __host__ __device__ constexpr int gram_stride() {
   return LPC * NA + (LPC < 32 ? LPC : 0);
 }
 
+// G (k x k) -> Gp (k x KP) zero-padded rows, so that every Gram row read is an aligned, unpredicated vector load
+template <typename T>
+__global__ void pad_gram_kernel(const T* __restrict__ G, int k, int kp, T* __restrict__ Gp) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= k * kp) return;
+  int a = idx / kp, i = idx - a * kp;
+  Gp[idx] = (i < k) ? G[(size_t)a * k + i] : T(0);
+}
+
 template <typename T, int LPC, int NA, int SMAX, bool GSM, bool MGLOB>
 __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
+  typedef typename VecOf<T>::type VT;
+  constexpr int VEC = VecOf<T>::N;
   constexpr int SA = SMAX / LPC;       // active slots per lane
   constexpr int GPW = 32 / LPC;        // columns per warp
-  constexpr int GS = gram_stride<LPC, NA>();
-  constexpr bool REFINE = (sizeof(T) == 4);
-  static_assert(SMAX % LPC == 0, "SMAX must be a multiple of LPC");
+  constexpr int KP = LPC * NA;
+  constexpr int GS = GSM ? gram_stride<LPC, NA>() : KP;   // row stride of the Gram copy this kernel reads
+  constexpr bool MASKED = (SMAX <= 64);   // slot occupancy kept in a 64-bit register mask
+  constexpr bool PACKED = (SMAX > 32);    // M stored as packed lower triangle
+  constexpr int UQ = (NA >= 16 || sizeof(T) == 8) ? 2 : 4;  // Gram rows in flight per correlation-pass batch
+  static_assert(SMAX % LPC == 0 && NA % VEC == 0, "bad tile shape");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = P.k;
@@ -124,21 +211,26 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
   const int warp = threadIdx.x >> 5;
   const int l = lane % LPC;
   const int gid = warp * GPW + lane / LPC;           // group id inside the CTA
+  const unsigned gmask = (LPC == 32) ? 0xffffffffu : (((1u << (LPC & 31)) - 1u) << ((lane / LPC) * LPC));
   uint32_t* gbase = reinterpret_cast<uint32_t*>(smem_raw + g_bytes) +
                     (size_t)gid * group_words<T, LPC, SMAX, MGLOB>();
-  T* Mg;
-  T* vecs;
+  constexpr int MELEMS = PACKED ? SMAX * (SMAX + 1) / 2 : SMAX * SMAX;
+  double* Mg;
+  double* vecs;
   if (MGLOB) {
-    Mg = P.Mscratch + ((size_t)blockIdx.x * (blockDim.x / LPC) + gid) * (size_t)SMAX * SMAX;
-    vecs = reinterpret_cast<T*>(gbase);
+    Mg = P.Mscratch + ((size_t)blockIdx.x * (blockDim.x / LPC) + gid) * (size_t)MELEMS;
+    vecs = reinterpret_cast<double*>(gbase);
   } else {
-    Mg = reinterpret_cast<T*>(gbase);
-    vecs = Mg + SMAX * SMAX;
+    Mg = reinterpret_cast<double*>(gbase);
+    vecs = Mg + MELEMS;
   }
-  T* gs = vecs;                 // g = G[active, j]   (also the refinement residual)
-  T* us = vecs + SMAX;          // u = M g            (also the dropped row of M)
-  T* ws = vecs + 2 * SMAX;      // equiangular weights by slot
-  int* acts = reinterpret_cast<int*>(vecs + 3 * SMAX);   // slot -> atom (-1 = free)
+  double* gs = vecs;                                   // g = G[active, j]   (also a copy of w at a drop)
+  double* us = vecs + SMAX;                            // u = M g            (also the dropped row of M)
+  SlotW<T>* sw_ = reinterpret_cast<SlotW<T>*>(vecs + 2 * SMAX);   // (atom, normalised weight) by slot
+  int* acts = reinterpret_cast<int*>(sw_ + SMAX);      // slot -> atom (-1 = free)
+
+  // atom owned by (lane l, register m): VEC consecutive atoms per lane per vector load
+  auto atom_of = [&](int m) -> int { return ((m / VEC) * LPC + l) * VEC + (m % VEC); };
 
   if (GSM) {
     for (int idx = threadIdx.x; idx < k * GS; idx += blockDim.x) {
@@ -147,14 +239,16 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
     }
     __syncthreads();
   }
-  auto Gat = [&](int a, int i) -> T {
-    if (GSM) return Gs[a * GS + i];
-    return (i < k) ? __ldg(P.G + (size_t)a * k + i) : T(0);
+  const T* Gr = GSM ? Gs : P.Gp;                       // padded rows, stride GS
+  auto Gat = [&](int a, int i) -> T { return Gr[(size_t)a * GS + i]; };
+  // M element (q, p): symmetric
+  auto Midx = [&](int q, int p) -> int {
+    if (PACKED) return (p <= q) ? q * (q + 1) / 2 + p : p * (p + 1) / 2 + q;
+    return q * SMAX + p;
   };
 
   const T tiny = T(1.1754943508222875e-38);      // np.finfo(np.float32).tiny
   const T eps32 = T(1.1920928955078125e-07);     // np.finfo(np.float32).eps  (equality_tolerance)
-  const T piv_floor = T(2.220446049250313e-16);  // LassoLars eps default
   const T dT = T(P.d);
   const T amin = P.amin;
 
@@ -177,21 +271,28 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
     unsigned inact = 0;
 #pragma unroll
     for (int m = 0; m < NA; ++m) {
-      int i = l + LPC * m;
+      int i = atom_of(m);
       bool ok = valid && i < k;
       cov[m] = ok ? crow[i] : T(0);
       if (ok) inact |= 1u << m;
     }
     T coef[SA], prev[SA];
+    double wd[SA];                       // unnormalised equiangular weights M 1, maintained incrementally
 #pragma unroll
-    for (int m = 0; m < SA; ++m) { coef[m] = T(0); prev[m] = T(0); }
+    for (int m = 0; m < SA; ++m) {
+      coef[m] = T(0); prev[m] = T(0); wd[m] = 0.0;
+      SlotW<T> z; z.atom = 0; z.w = T(0);
+      sw_[l + LPC * m] = z;
+      acts[l + LPC * m] = -1;
+    }
+    double sw = 0.0;                     // sum of wd (group-uniform)
     int n_iter = 0, n_act = 0, hw = 0, status = 0, max_act = 0;
+    unsigned long long occ = 0;          // occupied slots (MASKED variants)
     bool drop = false, done = !valid;
     int dslot = 0;
     T a_prev = T(0);
-    // the atom dropped by the last step: it is inactive from now on, but sklearn's prev_coef still holds
-    // its value at the previous knot, which matters when the path stops inside the segment that ended with
-    // the drop (the interpolation then lands on a point where the atom is still positive).
+    // the atom dropped by the last step: inactive from now on, but sklearn's prev_coef still holds its value
+    // at the previous knot, which matters when the path stops inside the segment that ended with the drop.
     int ghost_atom = -1;
     T ghost_prev = T(0), ghost_val = T(0);
 
@@ -203,14 +304,10 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
 #pragma unroll
       for (int m = 0; m < NA; ++m)
         if ((inact >> m) & 1u) {
-          if (cov[m] > best) { best = cov[m]; bi = l + LPC * m; }
+          const int i = atom_of(m);
+          if (cov[m] > best || (cov[m] == best && i < bi)) { best = cov[m]; bi = i; }
         }
-#pragma unroll
-      for (int off = LPC / 2; off > 0; off >>= 1) {
-        T ov = __shfl_xor_sync(0xffffffffu, best, off);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-      }
+      gargmax<LPC>(best, bi, gmask);
       const bool any_inact = (bi != 0x7fffffff);
       const T C = any_inact ? best : T(0);
       const T a_cur = C / dT;
@@ -233,92 +330,129 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
         }
       }
 
-      // ---- 2. atom j joins: border M ----
+      // ---- 2. atom j joins: border M, update w = M 1 incrementally ----
       if (__any_sync(0xffffffffu, do_add)) {
         const int j = bi;
-        int cand = 0x7fffffff;
+        int qn;
+        if (MASKED) {
+          qn = (~occ == 0ull) ? 64 : (__ffsll((long long)~occ) - 1);
+        } else {
+          int cand = 0x7fffffff;
 #pragma unroll
-        for (int m = 0; m < SA; ++m) {
-          int p = l + LPC * m;
-          if (do_add && p < hw && acts[p] < 0 && p < cand) cand = p;
+          for (int m = 0; m < SA; ++m) {
+            int p = l + LPC * m;
+            if (do_add && p < hw && acts[p] < 0 && p < cand) cand = p;
+          }
+          cand = __reduce_min_sync(gmask, cand);
+          qn = (cand == 0x7fffffff) ? hw : cand;
         }
-        cand = gmini<LPC>(cand);
-        const int qn = (cand == 0x7fffffff) ? hw : cand;
-        if (do_add && qn >= SMAX) {       // active set outgrew this variant: hand the column to the large path
+        if (do_add && qn >= SMAX) {       // active set outgrew this tier: hand the column to the next one
           status |= 8;
           done = true;
           do_add = false;
         }
-        T gj[SA], u[SA];
+        const int hwW = __reduce_max_sync(0xffffffffu, do_add ? hw : 0);
+        double gj[SA], u[SA];
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
-          int p = l + LPC * m;
-          T gv = T(0);
-          if (do_add && p < hw) {
-            int a = acts[p];
-            if (a >= 0) gv = Gat(a, j);
+          gj[m] = 0.0;
+          u[m] = 0.0;
+          if (LPC * m < hwW) {
+            int p = l + LPC * m;
+            T gv = T(0);
+            if (do_add && p < hw) {
+              int a = acts[p];
+              if (a >= 0) gv = Gat(a, j);
+            }
+            gj[m] = (double)gv;
+            gs[p] = (double)gv;
           }
-          gj[m] = gv;
-          gs[p] = gv;
-          u[m] = T(0);
         }
         __syncwarp();
-        const int hwW = __reduce_max_sync(0xffffffffu, do_add ? hw : 0);
-        for (int q = 0; q < hwW; ++q) {
-          const T gq = gs[q];
+        // u = M g
+        {
+          int qb = 0;
+#pragma unroll 2
+          for (int q = 0; q < hwW; ++q) {
+            const double gq = gs[q];
 #pragma unroll
-          for (int m = 0; m < SA; ++m) {
-            int p = l + LPC * m;
-            if (do_add && q < hw && p < hw) u[m] += Mg[q * SMAX + p] * gq;
+            for (int m = 0; m < SA; ++m) {
+              if (LPC * m < hwW) {
+                const int p = l + LPC * m;
+                const int idx = PACKED ? ((p <= q) ? qb + p : p * (p + 1) / 2 + q) : q * SMAX + p;
+                if (do_add && q < hw && p < hw) u[m] += Mg[idx] * gq;
+              }
+            }
+            qb += q + 1;
           }
         }
-        T part = T(0);
+        double part = 0.0, su = 0.0;
 #pragma unroll
-        for (int m = 0; m < SA; ++m) part += gj[m] * u[m];
-        const T Gjj = do_add ? Gat(j, j) : T(1);
-        const T sig = Gjj - gsum<T, LPC>(part);
-        T piv = sqrt(fabs(sig));
-        piv = piv > piv_floor ? piv : piv_floor;
-        bool degen = piv < T(1e-7);
-        if (REFINE) degen = degen || !(sig > T(4) * eps32 * Gjj);   // fp32: Schur complement below rounding noise
+        for (int m = 0; m < SA; ++m) { part += gj[m] * u[m]; su += u[m]; }
+#pragma unroll
+        for (int off = LPC / 2; off > 0; off >>= 1) {
+          part += __shfl_xor_sync(0xffffffffu, part, off);
+          su += __shfl_xor_sync(0xffffffffu, su, off);
+        }
+        const double Gjj = do_add ? (double)Gat(j, j) : 1.0;
+        const double sig = Gjj - part;
+        // sklearn: diag = max(sqrt(|c - v|), eps); degenerate if diag < 1e-7  <=>  |sig| < 1e-14
+        double asig = fabs(sig);
+        asig = asig > 4.930380657631324e-32 ? asig : 4.930380657631324e-32;
+        bool degen = asig < 1e-14;
+        if (sizeof(T) == 4) degen = degen || !(sig > 4.0 * (double)eps32 * Gjj);   // Schur complement below the rounding noise of an fp32 Gram
         if (do_add && degen) {
           // degenerate regressor (sklearn _least_angle.py:723-742): covariance zeroed, atom stays inactive
           status |= 1;
 #pragma unroll
           for (int m = 0; m < NA; ++m)
-            if (l + LPC * m == j) cov[m] = T(0);
+            if (atom_of(m) == j) cov[m] = T(0);
           do_add = false;
           skip = true;
         }
-        const T inv = T(1) / (piv * piv);
+        const double inv = fast_rcp(asig);
 #pragma unroll
-        for (int m = 0; m < SA; ++m) us[l + LPC * m] = u[m];
+        for (int m = 0; m < SA; ++m)
+          if (LPC * m < hwW) us[l + LPC * m] = u[m];
         __syncwarp();
-        for (int q = 0; q < hwW; ++q) {
-          const T uq = us[q] * inv;
+        // M += u u^T / sigma  (lower triangle only when packed)
+        {
+          int qb = 0;
+#pragma unroll 2
+          for (int q = 0; q < hwW; ++q) {
+            const double uq = us[q] * inv;
 #pragma unroll
-          for (int m = 0; m < SA; ++m) {
-            int p = l + LPC * m;
-            if (do_add && q < hw && p < hw) Mg[q * SMAX + p] += uq * u[m];
+            for (int m = 0; m < SA; ++m) {
+              if (LPC * m < hwW) {
+                const int p = l + LPC * m;
+                const int idx = PACKED ? qb + p : q * SMAX + p;
+                if (do_add && q < hw && (PACKED ? p <= q : p < hw)) Mg[idx] += uq * u[m];
+              }
+            }
+            qb += q + 1;
           }
         }
         __syncwarp();
         if (do_add) {
           const int hw_new = hw > qn + 1 ? hw : qn + 1;
+          const double tau = (1.0 - su) * inv;           // new entry of M 1
 #pragma unroll
           for (int m = 0; m < SA; ++m) {
             int p = l + LPC * m;
             if (p < hw_new) {
-              T val = (p == qn) ? inv : -u[m] * inv;
-              Mg[qn * SMAX + p] = val;
-              Mg[p * SMAX + qn] = val;
+              const double val = (p == qn) ? inv : -u[m] * inv;
+              Mg[Midx(qn, p)] = val;
+              if (!PACKED) Mg[Midx(p, qn)] = val;
+              wd[m] = (p == qn) ? tau : wd[m] - tau * u[m];
               if (p == qn) { coef[m] = T(0); prev[m] = T(0); acts[qn] = j; }
             }
           }
+          sw += tau * (1.0 - su);
 #pragma unroll
           for (int m = 0; m < NA; ++m)
-            if (l + LPC * m == j) inact &= ~(1u << m);
+            if (atom_of(m) == j) inact &= ~(1u << m);
           hw = hw_new;
+          if (MASKED) occ |= 1ull << qn;
           ++n_act;
           max_act = n_act > max_act ? n_act : max_act;
         }
@@ -332,68 +466,27 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
       }
       bool live = !done && !skip;
 
-      // ---- 4. equiangular weights w = AA * M 1 ----
-      const int hwL = __reduce_max_sync(0xffffffffu, live ? hw : 0);
-      T w[SA];
-#pragma unroll
-      for (int m = 0; m < SA; ++m) w[m] = T(0);
-      for (int q = 0; q < hwL; ++q) {
-#pragma unroll
-        for (int m = 0; m < SA; ++m) {
-          int p = l + LPC * m;
-          if (live && q < hw && p < hw) w[m] += Mg[q * SMAX + p];
-        }
-      }
-      if (REFINE) {
-        // one step of iterative refinement: w += M (1 - G_AA w)
-#pragma unroll
-        for (int m = 0; m < SA; ++m) ws[l + LPC * m] = w[m];
-        __syncwarp();
-        T r[SA];
-#pragma unroll
-        for (int m = 0; m < SA; ++m) {
-          int p = l + LPC * m;
-          T rr = T(0);
-          if (live && p < hw) {
-            int ap = acts[p];
-            if (ap >= 0) {
-              T acc = T(0);
-              for (int q = 0; q < hw; ++q) {
-                int aq = acts[q];
-                if (aq >= 0) acc += Gat(aq, ap) * ws[q];
-              }
-              rr = T(1) - acc;
-            }
-          }
-          r[m] = rr;
-        }
-#pragma unroll
-        for (int m = 0; m < SA; ++m) gs[l + LPC * m] = r[m];
-        __syncwarp();
-        for (int q = 0; q < hwL; ++q) {
-          const T rq = gs[q];
-#pragma unroll
-          for (int m = 0; m < SA; ++m) {
-            int p = l + LPC * m;
-            if (live && q < hw && p < hw) w[m] += Mg[q * SMAX + p] * rq;
-          }
-        }
-        __syncwarp();
-      }
-      T sw = T(0);
-#pragma unroll
-      for (int m = 0; m < SA; ++m) sw += w[m];
-      sw = gsum<T, LPC>(sw);
-      if (live && !(sw > T(0) && sw < Num<T>::big())) {   // active Gram block numerically singular
+      // ---- 4. normalise the equiangular weights: w = AA * M 1, AA = 1/sqrt(1^T M 1) ----
+      if (live && !(sw > 0.0 && sw < 1e300)) {   // active Gram block numerically singular
         status |= 16;
         done = true;
         live = false;
       }
-      const T AA = live ? T(1) / sqrt(sw) : T(1);
+      const int hwL = __reduce_max_sync(0xffffffffu, live ? hw : 0);
+      const double AAd = live ? fast_rsqrt(sw) : 1.0;
+      const T AA = (T)AAd;
+      T w[SA];
 #pragma unroll
       for (int m = 0; m < SA; ++m) {
-        w[m] *= AA;
-        ws[l + LPC * m] = live ? w[m] : T(0);
+        w[m] = (T)(wd[m] * AAd);
+        if (LPC * m < hwL) {
+          const int p = l + LPC * m;
+          if (live && p < hw) {
+            const int a = acts[p];
+            SlotW<T> e; e.atom = a >= 0 ? a : 0; e.w = a >= 0 ? w[m] : T(0);
+            sw_[p] = e;
+          }
+        }
       }
       __syncwarp();
 
@@ -401,13 +494,29 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
       T corr[NA];
 #pragma unroll
       for (int m = 0; m < NA; ++m) corr[m] = T(0);
-      for (int q = 0; q < hwL; ++q) {
-        const int a = (live && q < hw) ? acts[q] : -1;
-        if (a >= 0) {
-          const T wq = ws[q];
+      for (int q0 = 0; q0 < hwL; q0 += UQ) {
+        SlotW<T> e[UQ];
 #pragma unroll
-          for (int m = 0; m < NA; ++m) corr[m] += Gat(a, l + LPC * m) * wq;
+        for (int t = 0; t < UQ; ++t) {
+          const int q = q0 + t;
+          e[t] = sw_[q < SMAX ? q : SMAX - 1];
+          if (!(live && q < hw)) { e[t].atom = 0; e[t].w = T(0); }
         }
+        VT gv[UQ][NA / VEC];
+#pragma unroll
+        for (int t = 0; t < UQ; ++t) {
+          const VT* row = reinterpret_cast<const VT*>(Gr + (size_t)e[t].atom * GS) + l;
+#pragma unroll
+          for (int v = 0; v < NA / VEC; ++v) gv[t][v] = row[v * LPC];
+        }
+#pragma unroll
+        for (int t = 0; t < UQ; ++t)
+#pragma unroll
+          for (int v = 0; v < NA / VEC; ++v) {
+            const T* gp = reinterpret_cast<const T*>(&gv[t][v]);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) corr[v * VEC + c] += gp[c] * e[t].w;
+          }
       }
       if (sizeof(T) == 8) {
         // np.around(corr_eq_dir, decimals=15)  (sklearn _least_angle.py:806)
@@ -420,31 +529,28 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
 #pragma unroll
       for (int m = 0; m < NA; ++m)
         if ((inact >> m) & 1u) {
-          T v = (C - cov[m]) / (AA - corr[m] + tiny);
+          T v = qdiv(C - cov[m], AA - corr[m] + tiny);
           if (v > T(0) && v < g1) g1 = v;
         }
-      g1 = gmin<T, LPC>(g1);
+      g1 = gminpos<LPC>(g1, gmask);
       T gamma = C / AA;
       gamma = g1 < gamma ? g1 : gamma;
       T zbest = Num<T>::big();
-      int zs = 0x7fffffff;
+      int zs = -1;
 #pragma unroll
       for (int m = 0; m < SA; ++m) {
-        int p = l + LPC * m;
-        if (live && p < hw && acts[p] >= 0) {
-          T z = -coef[m] / (w[m] + tiny);
-          if (z > T(0) && z < zbest) { zbest = z; zs = p; }
+        if (LPC * m < hwL) {
+          int p = l + LPC * m;
+          if (live && p < hw && acts[p] >= 0) {
+            T z = qdiv(-coef[m], w[m] + tiny);
+            if (z > T(0) && z < zbest) { zbest = z; zs = p; }
+          }
         }
       }
-#pragma unroll
-      for (int off = LPC / 2; off > 0; off >>= 1) {
-        T ov = __shfl_xor_sync(0xffffffffu, zbest, off);
-        int oi = __shfl_xor_sync(0xffffffffu, zs, off);
-        if (ov < zbest || (ov == zbest && oi > zs && oi != 0x7fffffff)) { zbest = ov; zs = oi; }
-      }
+      gargminpos<LPC>(zbest, zs, gmask);
       if (live) {
         drop = false;
-        if (zbest < gamma) { gamma = zbest; drop = true; dslot = zs; }
+        if (zbest < gamma && zs >= 0) { gamma = zbest; drop = true; dslot = zs; }
         // ---- 7. move along the path ----
         ++n_iter;
         a_prev = a_cur;
@@ -462,73 +568,99 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
         st_s2 += (unsigned)(n_act * n_act);
       }
 
-      // ---- 8. atom leaves: Schur downdate of M, exact covariance of the dropped atom ----
+      // ---- 8. atom leaves: Schur downdate of M and of w, exact covariance of the dropped atom ----
       const bool dodrop = live && drop;
       if (__any_sync(0xffffffffu, dodrop)) {
         const int p0 = dodrop ? dslot : 0;
         const int a_d = dodrop ? acts[p0] : 0;
+        const int hwD = __reduce_max_sync(0xffffffffu, dodrop ? hw : 0);
+        double ur[SA];
+        double sur = 0.0;
+        T gp = T(0);
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
-          int p = l + LPC * m;
-          us[p] = (dodrop && p < hw) ? Mg[p0 * SMAX + p] : T(0);
+          ur[m] = 0.0;
+          if (LPC * m < hwD) {
+            int p = l + LPC * m;
+            ur[m] = (dodrop && p < hw) ? Mg[Midx(p0, p)] : 0.0;
+            us[p] = ur[m];
+            gs[p] = wd[m];
+            sur += ur[m];
+            if (dodrop && p == p0) gp = prev[m];
+          }
+        }
+#pragma unroll
+        for (int off = LPC / 2; off > 0; off >>= 1) {
+          sur += __shfl_xor_sync(0xffffffffu, sur, off);
+          gp += __shfl_xor_sync(0xffffffffu, gp, off);
         }
         __syncwarp();
-        const T mpp = dodrop ? us[p0] : T(1);
+        const double mpp = dodrop ? us[p0] : 1.0;
+        const double wp0 = dodrop ? gs[p0] : 0.0;
+        const double rmpp = fast_rcp(mpp);
+        if (dodrop) { ghost_atom = a_d; ghost_prev = gp; }
         {
-          T gp = T(0);
+          int qb = 0;
+#pragma unroll 2
+          for (int q = 0; q < hwD; ++q) {
+            const double f = us[q] * rmpp;
 #pragma unroll
-          for (int m = 0; m < SA; ++m)
-            if (dodrop && l + LPC * m == p0) gp = prev[m];
-          gp = gsum<T, LPC>(gp);
-          if (dodrop) { ghost_atom = a_d; ghost_prev = gp; }
-        }
-        const int hwD = __reduce_max_sync(0xffffffffu, dodrop ? hw : 0);
-        T ur[SA];
-#pragma unroll
-        for (int m = 0; m < SA; ++m) ur[m] = us[l + LPC * m];
-        for (int q = 0; q < hwD; ++q) {
-          const T f = us[q] / mpp;
-#pragma unroll
-          for (int m = 0; m < SA; ++m) {
-            int p = l + LPC * m;
-            if (dodrop && q < hw && p < hw) Mg[q * SMAX + p] -= f * ur[m];
+            for (int m = 0; m < SA; ++m) {
+              if (LPC * m < hwD) {
+                const int p = l + LPC * m;
+                const int idx = PACKED ? qb + p : q * SMAX + p;
+                if (dodrop && q < hw && (PACKED ? p <= q : p < hw)) Mg[idx] -= f * ur[m];
+              }
+            }
+            qb += q + 1;
           }
         }
         __syncwarp();
         if (dodrop) {
+          const double fw = wp0 * rmpp;
 #pragma unroll
           for (int m = 0; m < SA; ++m) {
             int p = l + LPC * m;
             if (p < hw) {
-              Mg[p0 * SMAX + p] = T(0);
-              Mg[p * SMAX + p0] = T(0);
+              Mg[Midx(p0, p)] = 0.0;
+              if (!PACKED) Mg[Midx(p, p0)] = 0.0;
+              wd[m] = (p == p0) ? 0.0 : wd[m] - fw * ur[m];
             }
-            if (p == p0) { coef[m] = T(0); prev[m] = T(0); acts[p0] = -1; }
+            if (p == p0) {
+              coef[m] = T(0); prev[m] = T(0); acts[p0] = -1;
+              SlotW<T> z; z.atom = 0; z.w = T(0);
+              sw_[p0] = z;
+            }
           }
+          sw = sw - wp0 - fw * (sur - mpp);
           --n_act;
           ++st_drops;
+          if (MASKED) occ &= ~(1ull << p0);
         }
         __syncwarp();
         int top = 0;
         T part = T(0);
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
-          int p = l + LPC * m;
-          if (dodrop && p < hw) {
-            int a = acts[p];
-            if (a >= 0) {
-              top = p + 1;
-              part += Gat(a_d, a) * coef[m];
+          if (LPC * m < hwD) {
+            int p = l + LPC * m;
+            if (dodrop && p < hw) {
+              int a = acts[p];
+              if (a >= 0) {
+                top = p + 1;
+                part += Gat(a_d, a) * coef[m];
+              }
             }
           }
         }
-        top = gmaxi<LPC>(top);
-        part = gsum<T, LPC>(part);
+        if (MASKED) top = (occ == 0ull) ? 0 : (64 - __clzll((long long)occ));
+        else top = __reduce_max_sync(gmask, top);
+        part = gsum<LPC>(part);
         if (dodrop) {
           hw = top;
 #pragma unroll
           for (int m = 0; m < NA; ++m)
-            if (l + LPC * m == a_d) {
+            if (atom_of(m) == a_d) {
               cov[m] = crow[a_d] - part;
               inact |= 1u << m;
             }
@@ -542,7 +674,7 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
       T* hrow = P.Ht + (size_t)col * k;
 #pragma unroll
       for (int m = 0; m < NA; ++m) {
-        int i = l + LPC * m;
+        int i = atom_of(m);
         if (i < k) hrow[i] = T(0);
       }
     }
@@ -565,7 +697,7 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
           unsigned slot = atomicAdd(P.ovf_count, 1u);
           P.ovf_list[slot] = col;
         }
-        ++st_ovf;
+        if (P.count_stats) ++st_ovf;
       } else {
         ++st_cols;
         if (status & ~8) ++st_flag;
@@ -576,7 +708,8 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
   }  // ticket loop
 
   if (P.stats && l == 0) {
-    // lanes other than the group leader carry zero counters except knots/s/s2 (group-uniform): leader only
+    // knots / active-set sums are executed work (a column re-walked by a later tier counts again);
+    // columns are counted once, by the tier that finishes them
     atomicAdd(&P.stats->columns, st_cols);
     atomicAdd(&P.stats->knots, st_knots);
     atomicAdd(&P.stats->sum_active, st_s);
@@ -593,84 +726,101 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
 // ------------------------------------------------------------------------------------------------
 
 struct LarsWs {           // header at the start of the caller's workspace
-  unsigned long long ticket_main;
-  unsigned long long ticket_ovf;
-  unsigned int ovf_count;
-  unsigned int pad[11];
+  unsigned long long ticket[3];
+  unsigned int ovf_count[2];
+  unsigned int pad[8];
 };
 static_assert(sizeof(LarsWs) == 64, "header size");
 
 static int k_class(int k) { return k <= 32 ? 0 : k <= 64 ? 1 : k <= 128 ? 2 : k <= 256 ? 3 : k <= 512 ? 4 : -1; }
 static int class_kp(int c) { static const int kp[5] = {32, 64, 128, 256, 512}; return kp[c]; }
-static int class_lpc(int c) { static const int v[5] = {8, 16, 32, 32, 32}; return v[c]; }
 
-static size_t ovf_scratch_groups(int kp, size_t tsz) {
-  size_t per = (size_t)kp * kp * tsz;
+static size_t ovf_scratch_groups(int kp) {
+  size_t per = (size_t)kp * (kp + 1) / 2 * sizeof(double);
   size_t g = (96ull << 20) / per;
   if (g < 16) g = 16;
   if (g > 592) g = 592;
   return g;
 }
 
-template <typename T, int LPC, int NA, int SMAX>
-static int launch_class(const T* G, const T* Ct, long long n, int k, int d, double alpha, int max_iter, T* Ht,
-                        unsigned char* ws, onmf_lars_stats* stats, cudaStream_t st) {
+template <typename T, int LPC, int NA, int SMAX, bool MGLOB>
+static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaStream_t st) {
   constexpr int GPW = 32 / LPC;
-  constexpr int KP = LPC * NA;
-  LarsWs* hdr = reinterpret_cast<LarsWs*>(ws);
-  long long* ovf_list = reinterpret_cast<long long*>(ws + sizeof(LarsWs));
-  size_t list_bytes = round_up<size_t>((size_t)n * sizeof(long long), 256);
-  T* mscr = reinterpret_cast<T*>(ws + sizeof(LarsWs) + list_bytes);
-  ONMF_CUDA(cudaMemsetAsync(hdr, 0, sizeof(LarsWs), st));
-
-  LarsParams<T> P;
-  P.G = G; P.Ct = Ct; P.Ht = Ht; P.n = n; P.k = k; P.d = d; P.max_iter = max_iter;
-  P.amin = T(alpha) / T(d);
-  P.ticket = &hdr->ticket_main; P.col_list = nullptr; P.n_list = nullptr;
-  P.ovf_list = ovf_list; P.ovf_count = &hdr->ovf_count; P.Mscratch = nullptr; P.stats = stats;
-
+  const int k = P.k;
   const int smem_max = max_smem_optin();
   const size_t g_bytes = round_up<size_t>((size_t)k * gram_stride<LPC, NA>() * sizeof(T), 128);
-  const size_t grp_bytes = (size_t)group_words<T, LPC, SMAX, false>() * 4;
-  const bool gsm = g_bytes <= 72 * 1024 && (smem_max - (long)g_bytes) >= (long)(2 * GPW * grp_bytes);
+  const size_t grp_bytes = (size_t)group_words<T, LPC, SMAX, MGLOB>() * 4;
+  const bool gsm = !MGLOB && g_bytes <= 72 * 1024 && (smem_max - (long)g_bytes - 256) >= (long)(2 * GPW * grp_bytes);
   const size_t avail = smem_max - (gsm ? g_bytes : 0) - 256;
   int nw = (int)(avail / (GPW * grp_bytes));
+  if (nw > max_warps) nw = max_warps;
   if (nw > 16) nw = 16;
   if (nw < 1) return fail(ONMF_E_UNSUPPORTED, "lasso_lars: shared memory too small for one warp");
   // spread small minibatches over all SMs instead of packing few CTAs
-  long long groups = cdiv<long long>(n, GPW);
+  long long groups = cdiv<long long>(n_upper, GPW);
   int nw_need = (int)cdiv<long long>(groups, num_sms());
   if (nw_need < nw) nw = nw_need < 1 ? 1 : nw_need;
-  int grid = (int)cdiv<long long>(groups, nw);
-  if (grid > num_sms()) grid = num_sms();
+  long long grid_ll = cdiv<long long>(groups, nw);
+  int grid = grid_ll > num_sms() ? num_sms() : (int)grid_ll;
+  if (MGLOB) {
+    long long cap = (long long)ovf_scratch_groups(LPC * NA) / (nw * GPW);
+    if (cap < 1) { nw = 1; cap = (long long)ovf_scratch_groups(LPC * NA) / GPW; }
+    if (grid > cap) grid = (int)cap;
+  }
   size_t smem = (gsm ? g_bytes : 0) + (size_t)nw * GPW * grp_bytes;
   if (gsm) {
-    auto kern = lars_kernel<T, LPC, NA, SMAX, true, false>;
+    auto kern = lars_kernel<T, LPC, NA, SMAX, true, MGLOB>;
     ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, nw * 32, smem, st>>>(P);
   } else {
-    auto kern = lars_kernel<T, LPC, NA, SMAX, false, false>;
+    auto kern = lars_kernel<T, LPC, NA, SMAX, false, MGLOB>;
     ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, nw * 32, smem, st>>>(P);
   }
   ONMF_LAUNCH_CHECK("lars_kernel");
+  return ONMF_OK;
+}
 
-  if (SMAX < KP) {
-    // large-active-set pass over the columns the main pass could not finish (device-side list)
+// workspace layout: [LarsWs | list1 (n x 8) | list2 (n x 8) | Gp (k x KP) | M scratch (last tier, k > 128)]
+static size_t ws_list_bytes(long long n) { return round_up<size_t>((size_t)n * sizeof(long long), 256); }
+static size_t ws_gp_bytes(int k, int kp) { return round_up<size_t>((size_t)k * kp * sizeof(double), 256); }
+
+// tiers: S0 slots, then S1 (0 = none), then S2 (0 = none; G2 => M in global scratch)
+template <typename T, int LPC, int NA, int S0, int S1, int S2, bool G2>
+static int launch_class(const T* G, const T* Ct, long long n, int k, int d, double alpha, int max_iter, T* Ht,
+                        unsigned char* ws, onmf_lars_stats* stats, cudaStream_t st) {
+  constexpr int KP = LPC * NA;
+  LarsWs* hdr = reinterpret_cast<LarsWs*>(ws);
+  const size_t lb = ws_list_bytes(n);
+  long long* list1 = reinterpret_cast<long long*>(ws + sizeof(LarsWs));
+  long long* list2 = reinterpret_cast<long long*>(ws + sizeof(LarsWs) + lb);
+  T* gp = reinterpret_cast<T*>(ws + sizeof(LarsWs) + 2 * lb);
+  double* mscr = reinterpret_cast<double*>(ws + sizeof(LarsWs) + 2 * lb + ws_gp_bytes(k, KP));
+  ONMF_CUDA(cudaMemsetAsync(hdr, 0, sizeof(LarsWs), st));
+  pad_gram_kernel<T><<<cdiv(k * KP, 256), 256, 0, st>>>(G, k, KP, gp);
+  ONMF_LAUNCH_CHECK("pad_gram_kernel");
+
+  LarsParams<T> P;
+  P.G = G; P.Gp = gp; P.Ct = Ct; P.Ht = Ht; P.n = n; P.k = k; P.d = d; P.max_iter = max_iter;
+  P.amin = T(alpha) / T(d);
+  P.ticket = &hdr->ticket[0]; P.col_list = nullptr; P.n_list = nullptr;
+  P.ovf_list = S1 ? list1 : nullptr; P.ovf_count = &hdr->ovf_count[0]; P.Mscratch = nullptr; P.stats = stats;
+  P.count_stats = 1;
+  int rc = launch_tier<T, LPC, NA, S0, false>(P, n, 16, st);
+  if (rc) return rc;
+  if constexpr (S1 > 0) {
     LarsParams<T> Q = P;
-    Q.ticket = &hdr->ticket_ovf; Q.col_list = ovf_list; Q.n_list = &hdr->ovf_count;
-    Q.ovf_list = nullptr; Q.ovf_count = nullptr; Q.Mscratch = mscr;
-    size_t ng = ovf_scratch_groups(KP, sizeof(T));
-    const int nw2 = 2;
-    int grid2 = (int)(ng / (nw2 * GPW));
-    if (grid2 < 1) grid2 = 1;
-    long long need = cdiv<long long>(n, nw2 * GPW);
-    if (grid2 > need) grid2 = (int)need;
-    size_t smem2 = (size_t)nw2 * GPW * group_words<T, LPC, KP, true>() * 4;
-    auto kern2 = lars_kernel<T, LPC, NA, KP, false, true>;
-    ONMF_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    kern2<<<grid2, nw2 * 32, smem2, st>>>(Q);
-    ONMF_LAUNCH_CHECK("lars_kernel(overflow)");
+    Q.ticket = &hdr->ticket[1]; Q.col_list = list1; Q.n_list = &hdr->ovf_count[0];
+    Q.ovf_list = S2 ? list2 : nullptr; Q.ovf_count = &hdr->ovf_count[1]; Q.count_stats = 0;
+    rc = launch_tier<T, LPC, NA, S1, false>(Q, n, 16, st);
+    if (rc) return rc;
+    if constexpr (S2 > 0) {
+      LarsParams<T> R = P;
+      R.ticket = &hdr->ticket[2]; R.col_list = list2; R.n_list = &hdr->ovf_count[1];
+      R.ovf_list = nullptr; R.ovf_count = nullptr; R.Mscratch = G2 ? mscr : nullptr; R.count_stats = 0;
+      rc = launch_tier<T, LPC, NA, S2, G2>(R, n, G2 ? 2 : 16, st);
+      if (rc) return rc;
+    }
   }
   return ONMF_OK;
 }
@@ -680,11 +830,11 @@ static int lasso_lars_t(const void* G, const void* Ct, long long n, int k, int d
                         void* Ht, void* ws, onmf_lars_stats* stats, cudaStream_t st) {
   const T* g = (const T*)G; const T* c = (const T*)Ct; T* h = (T*)Ht; unsigned char* w = (unsigned char*)ws;
   switch (k_class(k)) {
-    case 0: return launch_class<T, 8, 4, 32>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 1: return launch_class<T, 16, 4, 64>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 2: return launch_class<T, 32, 4, 64>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 3: return launch_class<T, 32, 8, 64>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 4: return launch_class<T, 32, 16, 64>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
+    case 0: return launch_class<T, 8, 4, 32, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
+    case 1: return launch_class<T, 16, 4, 32, 64, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
+    case 2: return launch_class<T, 32, 4, 32, 64, 128, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
+    case 3: return launch_class<T, 32, 8, 64, 128, 256, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
+    case 4: return launch_class<T, 32, 16, 64, 128, 512, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
   }
   return fail(ONMF_E_UNSUPPORTED, "lasso_lars: n_components > 512 not instantiated");
 }
@@ -694,11 +844,10 @@ static int lasso_lars_t(const void* G, const void* Ct, long long n, int k, int d
 extern "C" size_t onmf_lasso_lars_workspace(int dtype, int k, int64_t n) {
   int c = onmf::k_class(k);
   if (c < 0 || n < 0) return 0;
-  size_t tsz = dtype == ONMF_F64 ? 8 : 4;
+  (void)dtype;
   int kp = onmf::class_kp(c);
-  size_t bytes = sizeof(onmf::LarsWs) + onmf::round_up<size_t>((size_t)n * sizeof(long long), 256);
-  int smax_main = c == 0 ? 32 : 64;
-  if (smax_main < kp) bytes += onmf::ovf_scratch_groups(kp, tsz) * (size_t)kp * kp * tsz;
+  size_t bytes = sizeof(onmf::LarsWs) + 2 * onmf::ws_list_bytes(n) + onmf::ws_gp_bytes(k, kp);
+  if (kp > 128) bytes += onmf::ovf_scratch_groups(kp) * ((size_t)kp * (kp + 1) / 2) * sizeof(double);
   return bytes + 256;
 }
 

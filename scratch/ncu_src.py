@@ -1,0 +1,24 @@
+import csv, subprocess, sys, io
+rep=sys.argv[1]; top=int(sys.argv[2]) if len(sys.argv)>2 else 45
+src = subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass'],capture_output=True,text=True).stdout
+rows=list(csv.reader(io.StringIO(src)))
+hi=[i for i,r in enumerate(rows) if len(r)>5 and r[0]=='Line No' and '# Samples' in r][0]
+h=rows[hi]; ci=h.index('# Samples'); ii=h.index('Instructions Executed')
+agg={}
+cur=None
+for r in rows[hi+1:]:
+    if len(r)<=ii: continue
+    if r[0]=='Line No': break
+    if r[0].strip().isdigit():
+        ln=int(r[0]); 
+        try: s=float(r[ci] or 0); ie=float(r[ii] or 0)
+        except: continue
+        if ln not in agg: agg[ln]=[0,0,r[1]]
+        # rows with line number: either the source line summary (Address empty) or sass rows
+        if r[2] in ('','-'):
+            agg[ln][0]=s; agg[ln][1]=ie
+tot_s=sum(v[0] for v in agg.values()); tot_i=sum(v[1] for v in agg.values())
+print('total samples %d, total warp-instructions %.3g'%(tot_s,tot_i))
+print('--- by samples')
+for ln,(s,ie,t) in sorted(agg.items(), key=lambda x:-x[1][0])[:top]:
+    print(f"{100*s/tot_s:5.1f}% smp {100*ie/tot_i:5.1f}% inst  L{ln:4d}: {t.strip()[:105]}")
