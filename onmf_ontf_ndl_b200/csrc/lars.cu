@@ -167,7 +167,8 @@ template <> struct __align__(16) SlotW<double> { int atom; int pad; double w; };
 template <typename T, int LPC, int SMAX, bool MGLOB>
 __host__ __device__ constexpr int group_words() {
   int mwords = (SMAX > 32) ? SMAX * (SMAX + 1) : 2 * SMAX * SMAX;
-  int w = (MGLOB ? 0 : mwords) + 4 * SMAX + SMAX * (int)(sizeof(SlotW<T>) / 4) + SMAX;
+  int sv = (SMAX + LPC - 1) / LPC * LPC;
+  int w = (MGLOB ? 0 : mwords) + 4 * sv + sv * (int)(sizeof(SlotW<T>) / 4) + sv;
   w = (w + 3) & ~3;                       // keep 16-byte alignment of the next group
   if (LPC < 32) {                         // start consecutive groups of a warp 2*LPC banks apart
     int r = w % 32;
@@ -194,14 +195,15 @@ template <typename T, int LPC, int NA, int SMAX, bool GSM, bool MGLOB>
 __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
   typedef typename VecOf<T>::type VT;
   constexpr int VEC = VecOf<T>::N;
-  constexpr int SA = SMAX / LPC;       // active slots per lane
+  constexpr int SA = (SMAX + LPC - 1) / LPC;   // active slots per lane
+  constexpr int SV = SA * LPC;                 // length of the per-slot vectors (>= SMAX)
   constexpr int GPW = 32 / LPC;        // columns per warp
   constexpr int KP = LPC * NA;
   constexpr int GS = GSM ? gram_stride<LPC, NA>() : KP;   // row stride of the Gram copy this kernel reads
   constexpr bool MASKED = (SMAX <= 64);   // slot occupancy kept in a 64-bit register mask
   constexpr bool PACKED = (SMAX > 32);    // M stored as packed lower triangle
   constexpr int UQ = (NA >= 16 || sizeof(T) == 8) ? 2 : 4;  // Gram rows in flight per correlation-pass batch
-  static_assert(SMAX % LPC == 0 && NA % VEC == 0, "bad tile shape");
+  static_assert(NA % VEC == 0 && SMAX % 4 == 0, "bad tile shape");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = P.k;
@@ -225,9 +227,9 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
     vecs = Mg + MELEMS;
   }
   double* gs = vecs;                                   // g = G[active, j]   (also a copy of w at a drop)
-  double* us = vecs + SMAX;                            // u = M g            (also the dropped row of M)
-  SlotW<T>* sw_ = reinterpret_cast<SlotW<T>*>(vecs + 2 * SMAX);   // (atom, normalised weight) by slot
-  int* acts = reinterpret_cast<int*>(sw_ + SMAX);      // slot -> atom (-1 = free)
+  double* us = vecs + SV;                              // u = M g            (also the dropped row of M)
+  SlotW<T>* sw_ = reinterpret_cast<SlotW<T>*>(vecs + 2 * SV);     // (atom, normalised weight) by slot
+  int* acts = reinterpret_cast<int*>(sw_ + SV);        // slot -> atom (-1 = free)
 
   // atom owned by (lane l, register m): VEC consecutive atoms per lane per vector load
   auto atom_of = [&](int m) -> int { return ((m / VEC) * LPC + l) * VEC + (m % VEC); };
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
     __syncthreads();
   }
   const T* Gr = GSM ? Gs : P.Gp;                       // padded rows, stride GS
-  auto Gat = [&](int a, int i) -> T { return Gr[(size_t)a * GS + i]; };
+  auto Gat = [&](int a, int i) -> T { return Gr[a * GS + i]; };
   // M element (q, p): symmetric
   auto Midx = [&](int q, int p) -> int {
     if (PACKED) return (p <= q) ? q * (q + 1) / 2 + p : p * (p + 1) / 2 + q;
@@ -371,6 +373,9 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
         __syncwarp();
         // u = M g
         {
+          int rb[SA];
+#pragma unroll
+          for (int m = 0; m < SA; ++m) { const int p = l + LPC * m; rb[m] = p * (p + 1) / 2; }
           int qb = 0;
 #pragma unroll 2
           for (int q = 0; q < hwW; ++q) {
@@ -379,8 +384,9 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
             for (int m = 0; m < SA; ++m) {
               if (LPC * m < hwW) {
                 const int p = l + LPC * m;
-                const int idx = PACKED ? ((p <= q) ? qb + p : p * (p + 1) / 2 + q) : q * SMAX + p;
-                if (do_add && q < hw && p < hw) u[m] += Mg[idx] * gq;
+                const int idx = PACKED ? ((p <= q) ? qb + p : rb[m] + q) : q * SMAX + p;
+                const bool on = (LPC == 32) ? (p < hw) : (do_add && q < hw && p < hw);
+                if (on) u[m] += Mg[idx] * gq;
               }
             }
             qb += q + 1;
@@ -426,7 +432,8 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
               if (LPC * m < hwW) {
                 const int p = l + LPC * m;
                 const int idx = PACKED ? qb + p : q * SMAX + p;
-                if (do_add && q < hw && (PACKED ? p <= q : p < hw)) Mg[idx] += uq * u[m];
+                const bool on = (LPC == 32) ? (PACKED ? p <= q : p < hw) : (do_add && q < hw && (PACKED ? p <= q : p < hw));
+                if (on) Mg[idx] += uq * u[m];
               }
             }
             qb += q + 1;
@@ -495,17 +502,14 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
 #pragma unroll
       for (int m = 0; m < NA; ++m) corr[m] = T(0);
       for (int q0 = 0; q0 < hwL; q0 += UQ) {
+        // free slots (and slots beyond this group's high-water mark) hold (atom 0, weight 0): no masking needed
         SlotW<T> e[UQ];
 #pragma unroll
-        for (int t = 0; t < UQ; ++t) {
-          const int q = q0 + t;
-          e[t] = sw_[q < SMAX ? q : SMAX - 1];
-          if (!(live && q < hw)) { e[t].atom = 0; e[t].w = T(0); }
-        }
+        for (int t = 0; t < UQ; ++t) e[t] = sw_[q0 + t];
         VT gv[UQ][NA / VEC];
 #pragma unroll
         for (int t = 0; t < UQ; ++t) {
-          const VT* row = reinterpret_cast<const VT*>(Gr + (size_t)e[t].atom * GS) + l;
+          const VT* row = reinterpret_cast<const VT*>(Gr + e[t].atom * GS) + l;
 #pragma unroll
           for (int v = 0; v < NA / VEC; ++v) gv[t][v] = row[v * LPC];
         }
@@ -609,7 +613,8 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
               if (LPC * m < hwD) {
                 const int p = l + LPC * m;
                 const int idx = PACKED ? qb + p : q * SMAX + p;
-                if (dodrop && q < hw && (PACKED ? p <= q : p < hw)) Mg[idx] -= f * ur[m];
+                const bool on = (LPC == 32) ? (PACKED ? p <= q : p < hw) : (dodrop && q < hw && (PACKED ? p <= q : p < hw));
+                if (on) Mg[idx] -= f * ur[m];
               }
             }
             qb += q + 1;
@@ -726,9 +731,9 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
 // ------------------------------------------------------------------------------------------------
 
 struct LarsWs {           // header at the start of the caller's workspace
-  unsigned long long ticket[3];
-  unsigned int ovf_count[2];
-  unsigned int pad[8];
+  unsigned long long ticket[4];
+  unsigned int ovf_count[4];
+  unsigned int pad[4];
 };
 static_assert(sizeof(LarsWs) == 64, "header size");
 
@@ -785,15 +790,15 @@ static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaSt
 static size_t ws_list_bytes(long long n) { return round_up<size_t>((size_t)n * sizeof(long long), 256); }
 static size_t ws_gp_bytes(int k, int kp) { return round_up<size_t>((size_t)k * kp * sizeof(double), 256); }
 
-// tiers: S0 slots, then S1 (0 = none), then S2 (0 = none; G2 => M in global scratch)
-template <typename T, int LPC, int NA, int S0, int S1, int S2, bool G2>
+// tiers: S0 slots, then S1, S2, S3 (0 = none); the last non-zero tier keeps M in global scratch when GL
+template <typename T, int LPC, int NA, int S0, int S1, int S2, int S3, bool GL>
 static int launch_class(const T* G, const T* Ct, long long n, int k, int d, double alpha, int max_iter, T* Ht,
                         unsigned char* ws, onmf_lars_stats* stats, cudaStream_t st) {
   constexpr int KP = LPC * NA;
   LarsWs* hdr = reinterpret_cast<LarsWs*>(ws);
   const size_t lb = ws_list_bytes(n);
-  long long* list1 = reinterpret_cast<long long*>(ws + sizeof(LarsWs));
-  long long* list2 = reinterpret_cast<long long*>(ws + sizeof(LarsWs) + lb);
+  long long* lists[2] = {reinterpret_cast<long long*>(ws + sizeof(LarsWs)),
+                         reinterpret_cast<long long*>(ws + sizeof(LarsWs) + lb)};
   T* gp = reinterpret_cast<T*>(ws + sizeof(LarsWs) + 2 * lb);
   double* mscr = reinterpret_cast<double*>(ws + sizeof(LarsWs) + 2 * lb + ws_gp_bytes(k, KP));
   ONMF_CUDA(cudaMemsetAsync(hdr, 0, sizeof(LarsWs), st));
@@ -803,24 +808,32 @@ static int launch_class(const T* G, const T* Ct, long long n, int k, int d, doub
   LarsParams<T> P;
   P.G = G; P.Gp = gp; P.Ct = Ct; P.Ht = Ht; P.n = n; P.k = k; P.d = d; P.max_iter = max_iter;
   P.amin = T(alpha) / T(d);
-  P.ticket = &hdr->ticket[0]; P.col_list = nullptr; P.n_list = nullptr;
-  P.ovf_list = S1 ? list1 : nullptr; P.ovf_count = &hdr->ovf_count[0]; P.Mscratch = nullptr; P.stats = stats;
-  P.count_stats = 1;
-  int rc = launch_tier<T, LPC, NA, S0, false>(P, n, 16, st);
+  P.Mscratch = nullptr; P.stats = stats;
+  // tier t reads list (t-1)&1 and appends to list t&1
+  auto tier_params = [&](int t, bool has_next, bool glob) {
+    LarsParams<T> Q = P;
+    Q.ticket = &hdr->ticket[t];
+    Q.col_list = t ? lists[(t - 1) & 1] : nullptr;
+    Q.n_list = t ? &hdr->ovf_count[t - 1] : nullptr;
+    Q.ovf_list = has_next ? lists[t & 1] : nullptr;
+    Q.ovf_count = &hdr->ovf_count[t];
+    Q.Mscratch = glob ? mscr : nullptr;
+    Q.count_stats = t == 0;
+    return Q;
+  };
+  int rc = launch_tier<T, LPC, NA, S0, (GL && S1 == 0)>(tier_params(0, S1 > 0, GL && S1 == 0), n, 16, st);
   if (rc) return rc;
   if constexpr (S1 > 0) {
-    LarsParams<T> Q = P;
-    Q.ticket = &hdr->ticket[1]; Q.col_list = list1; Q.n_list = &hdr->ovf_count[0];
-    Q.ovf_list = S2 ? list2 : nullptr; Q.ovf_count = &hdr->ovf_count[1]; Q.count_stats = 0;
-    rc = launch_tier<T, LPC, NA, S1, false>(Q, n, 16, st);
+    rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(tier_params(1, S2 > 0, GL && S2 == 0), n, (GL && S2 == 0) ? 2 : 16, st);
     if (rc) return rc;
-    if constexpr (S2 > 0) {
-      LarsParams<T> R = P;
-      R.ticket = &hdr->ticket[2]; R.col_list = list2; R.n_list = &hdr->ovf_count[1];
-      R.ovf_list = nullptr; R.ovf_count = nullptr; R.Mscratch = G2 ? mscr : nullptr; R.count_stats = 0;
-      rc = launch_tier<T, LPC, NA, S2, G2>(R, n, G2 ? 2 : 16, st);
-      if (rc) return rc;
-    }
+  }
+  if constexpr (S2 > 0) {
+    rc = launch_tier<T, LPC, NA, S2, (GL && S3 == 0)>(tier_params(2, S3 > 0, GL && S3 == 0), n, (GL && S3 == 0) ? 2 : 16, st);
+    if (rc) return rc;
+  }
+  if constexpr (S3 > 0) {
+    rc = launch_tier<T, LPC, NA, S3, GL>(tier_params(3, false, GL), n, GL ? 2 : 16, st);
+    if (rc) return rc;
   }
   return ONMF_OK;
 }
@@ -830,11 +843,11 @@ static int lasso_lars_t(const void* G, const void* Ct, long long n, int k, int d
                         void* Ht, void* ws, onmf_lars_stats* stats, cudaStream_t st) {
   const T* g = (const T*)G; const T* c = (const T*)Ct; T* h = (T*)Ht; unsigned char* w = (unsigned char*)ws;
   switch (k_class(k)) {
-    case 0: return launch_class<T, 8, 4, 32, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 1: return launch_class<T, 16, 4, 32, 64, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 2: return launch_class<T, 32, 4, 32, 64, 128, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 3: return launch_class<T, 32, 8, 64, 128, 256, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 4: return launch_class<T, 32, 16, 64, 128, 512, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
+    case 0: return launch_class<T, 8, 4, 32, 0, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
+    case 1: return launch_class<T, 16, 4, 32, 64, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
+    case 2: return launch_class<T, 32, 4, 32, 64, 128, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
+    case 3: return launch_class<T, 32, 8, 40, 64, 128, 256, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
+    case 4: return launch_class<T, 32, 16, 40, 64, 128, 512, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
   }
   return fail(ONMF_E_UNSUPPORTED, "lasso_lars: n_components > 512 not instantiated");
 }
