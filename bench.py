@@ -185,7 +185,7 @@ def run_ours(args):
     eng = OnmfEngine(d, k, alpha=alpha, dtype=dt, device=dev, process_group=dist.group.WORLD if world > 1 else None,
                      collect_stats=True)
     eng.set_state(W0)
-    Xb = torch.empty(n, d, dtype=dt, device=dev)
+    Xb = None if eng.use_tc else torch.empty(n, d, dtype=dt, device=dev)
     main = eng.main
 
     def barrier():
@@ -195,8 +195,13 @@ def run_ours(args):
 
     def one_step(t):
         idx = torch.randint(0, n, (n,), device=dev, generator=gen)     # fresh minibatch: resample the pool (with replacement)
-        _lib.gather_rows(pool, idx, Xb)
-        eng.step(Xb, float(t))
+        if eng.use_tc:
+            hi, lo = eng.split_buffers(n)
+            _lib.gather_rows_split(pool, idx, hi, lo)                   # K1 fused with the TF32 hi/lo split
+            eng.step(None, float(t), n=n)
+        else:
+            _lib.gather_rows(pool, idx, Xb)
+            eng.step(Xb, float(t))
 
     t = 0
     for _ in range(Wm):

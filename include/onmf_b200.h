@@ -124,6 +124,24 @@ int onmf_xxt_partial(int dtype, const void* Xt, int64_t n, int d, void* P2, void
 int onmf_axpby(int dtype, int64_t count, double a, const void* x, double b, void* y, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K2 / K4 on the tensor cores (fp32 only): TMA-fed tcgen05.mma kind::tf32 with TMEM accumulators and a
+ * 3xTF32 operand split (hi = rna_tf32(x), lo = x - hi; hi*hi + hi*lo + lo*hi) for fp32-class accuracy.
+ * Same products as onmf_cov / onmf_surrogate_partial above; operands are passed pre-split.
+ * onmf_tc_supported(k, d) != 0 when the shapes satisfy TMA's 16-byte stride rule (k % 4 == 0, d % 4 == 0).
+ * ------------------------------------------------------------------------------------------- */
+int onmf_tc_supported(int k, int d);
+int onmf_split_tf32(const void* src, void* hi, void* lo, int64_t count, void* stream);
+/* fused minibatch gather + split: (hi, lo)[j, :] = split(pool[idx[j], :]) */
+int onmf_gather_rows_split(const void* pool, int64_t n_pool, int d, const int64_t* idx, int64_t n, void* hi,
+                           void* lo, void* stream);
+int onmf_cov_tc(const void* Xt_hi, const void* Xt_lo, int64_t n, int d, const void* W_hi, const void* W_lo,
+                int k, void* Ct, void* stream);
+size_t onmf_surrogate_tc_workspace(int64_t n, int k, int d);
+int onmf_surrogate_partial_tc(const void* Ht_hi, const void* Ht_lo, const void* Xt_hi, const void* Xt_lo,
+                              int64_t n, int k, int d, void* P, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K5  dictionary update (one block-coordinate-descent sweep)
  * replaces: update_dict  src/ontf.py:91-115 == src/onmf.py:92-116
  *   for j in 0..k-1:  W[:,j] -= (W A[:,j] - B[j,:]^T) / (A[j,j] + 1);  W[:,j] = max(W[:,j], 0);

@@ -47,6 +47,12 @@ SIGNATURES = {
     "onmf_surrogate_blend": (_i, [_i, _vp, _i, _i, _dbl, _vp, _vp, _vp]),
     "onmf_xxt_partial": (_i, [_i, _vp, _i64, _i, _vp, _vp, _sz, _vp]),
     "onmf_axpby": (_i, [_i, _i64, _dbl, _vp, _dbl, _vp, _vp]),
+    "onmf_tc_supported": (_i, [_i, _i]),
+    "onmf_split_tf32": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "onmf_gather_rows_split": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp, _vp]),
+    "onmf_cov_tc": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp]),
+    "onmf_surrogate_tc_workspace": (_sz, [_i64, _i, _i]),
+    "onmf_surrogate_partial_tc": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _vp]),
     "onmf_update_dict": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "onmf_pgd_sweep": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _vp, _vp]),
 }
@@ -204,3 +210,45 @@ def pgd_sweep(G, Ct, alpha, it, Ht, stream=None):
     _check(load().onmf_pgd_sweep(dt(G), _ptr(G), _ptr(Ct), n, k, float(alpha), int(it), _ptr(Ht), _stream(stream)),
            "onmf_pgd_sweep")
     return Ht
+
+
+# ---- tensor-core (3xTF32) path ---------------------------------------------------------------
+
+def tc_supported(k, d):
+    return bool(load().onmf_tc_supported(int(k), int(d)))
+
+
+def split_tf32(src, hi, lo, stream=None):
+    _req(src, "src", torch.float32); _req(hi, "hi", torch.float32); _req(lo, "lo", torch.float32)
+    _check(load().onmf_split_tf32(_ptr(src), _ptr(hi), _ptr(lo), src.numel(), _stream(stream)), "onmf_split_tf32")
+
+
+def gather_rows_split(pool, idx, hi, lo, stream=None):
+    _req(pool, "pool", torch.float32); _req(idx, "idx", torch.int64); _req(hi, "hi", torch.float32); _req(lo, "lo", torch.float32)
+    if idx.shape[0] == 0:
+        return
+    _check(load().onmf_gather_rows_split(_ptr(pool), pool.shape[0], pool.shape[1], _ptr(idx), idx.shape[0], _ptr(hi), _ptr(lo),
+                                         _stream(stream)), "onmf_gather_rows_split")
+
+
+def cov_tc(Xhi, Xlo, Whi, Wlo, Ct, stream=None):
+    for t, nm in ((Xhi, "Xhi"), (Xlo, "Xlo"), (Whi, "Whi"), (Wlo, "Wlo"), (Ct, "Ct")):
+        _req(t, nm, torch.float32)
+    n, d = Xhi.shape
+    _check(load().onmf_cov_tc(_ptr(Xhi), _ptr(Xlo), n, d, _ptr(Whi), _ptr(Wlo), Whi.shape[1], _ptr(Ct), _stream(stream)), "onmf_cov_tc")
+    return Ct
+
+
+def surrogate_tc_workspace(n, k, d):
+    return int(load().onmf_surrogate_tc_workspace(n, k, d))
+
+
+def surrogate_partial_tc(Hhi, Hlo, Xhi, Xlo, P, workspace, stream=None):
+    for t, nm in ((Hhi, "Hhi"), (Hlo, "Hlo"), (Xhi, "Xhi"), (Xlo, "Xlo"), (P, "P")):
+        _req(t, nm, torch.float32)
+    _req(workspace, "workspace", torch.uint8)
+    n, k = Hhi.shape
+    d = Xhi.shape[1]
+    _check(load().onmf_surrogate_partial_tc(_ptr(Hhi), _ptr(Hlo), _ptr(Xhi), _ptr(Xlo), n, k, d, _ptr(P), _ptr(workspace),
+                                            workspace.numel(), _stream(stream)), "onmf_surrogate_partial_tc")
+    return P

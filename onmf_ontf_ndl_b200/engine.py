@@ -27,7 +27,7 @@ from . import _lib
 class OnmfEngine:
     def __init__(self, d: int, k: int, alpha: float = 1.0, beta: Optional[float] = None,
                  dtype: torch.dtype = torch.float32, device=None, max_iter: int = 1000,
-                 process_group=None, track_C: bool = False, collect_stats: bool = False):
+                 process_group=None, track_C: bool = False, collect_stats: bool = False, use_tc=None):
         if not torch.cuda.is_available():
             raise _lib.OnmfKernelError("OnmfEngine needs a CUDA device (there is no CPU path)")
         _lib.load()
@@ -54,6 +54,12 @@ class OnmfEngine:
         self.P2 = torch.zeros(d, d, dtype=dt_, device=dev) if track_C else None
         self._cap = 0
         self.Ct = self.Ht = self._ws_lars = self._ws_sur = None
+        # tensor-core (tcgen05, 3xTF32) path for the three large products; fp32 + TMA-friendly shapes only
+        self.use_tc = bool(use_tc if use_tc is not None else True) and dtype == torch.float32 and _lib.tc_supported(k, d)
+        if self.use_tc:
+            self.Whi = torch.empty(d, k, dtype=dt_, device=dev)
+            self.Wlo = torch.empty(d, k, dtype=dt_, device=dev)
+        self.Xhi = self.Xlo = self.Hhi = self.Hlo = None
         self.stats = torch.zeros(len(_lib.STATS_FIELDS), dtype=torch.int64, device=dev) if collect_stats else None
         self.main = torch.cuda.current_stream(dev)
         self.side = torch.cuda.Stream(dev)
@@ -86,6 +92,12 @@ class OnmfEngine:
         nbytes = _lib.surrogate_workspace(dt_, self._cap, self.k, self.d)
         if self.track_C:
             nbytes = max(nbytes, 64 * self.d * self.d * self.W.element_size() + 256)
+        if self.use_tc:
+            nbytes = max(nbytes, _lib.surrogate_tc_workspace(self._cap, self.k, self.d))
+            self.Xhi = torch.empty(self._cap, self.d, dtype=dt_, device=dev)
+            self.Xlo = torch.empty(self._cap, self.d, dtype=dt_, device=dev)
+            self.Hhi = torch.empty(self._cap, self.k, dtype=dt_, device=dev)
+            self.Hlo = torch.empty(self._cap, self.k, dtype=dt_, device=dev)
         self._ws_sur = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
     def _stats_ptr(self):
@@ -100,7 +112,13 @@ class OnmfEngine:
         Ct = self.Ct[:n]
         Ht = self.Ht[:n] if out is None else out
         _lib.gram(W, self.G)
-        _lib.cov(Xt, W, Ct)
+        if self.use_tc and n > 0:
+            _lib.split_tf32(Xt, self.Xhi[:n], self.Xlo[:n])
+            _lib.split_tf32(W, self.Whi, self.Wlo)
+            _lib.cov_tc(self.Xhi[:n], self.Xlo[:n], self.Whi, self.Wlo, Ct)
+            self.launches += 2
+        else:
+            _lib.cov(Xt, W, Ct)
         _lib.lasso_lars(self.G, Ct, self.d, self.alpha if alpha is None else alpha, Ht, self._ws_lars,
                         max_iter=self.max_iter, stats=self._stats_ptr())
         self.launches += 4
@@ -111,11 +129,21 @@ class OnmfEngine:
         """Same as step() but with externally computed codes Ht (n x k), e.g. from the PGD coder."""
         return self.step(Xt, t, codes=Ht)
 
-    def step(self, Xt: torch.Tensor, t: float, codes: Optional[torch.Tensor] = None):
+    def split_buffers(self, n):
+        """(Xhi, Xlo) views of the engine-owned pre-split minibatch buffers (tensor-core path): a producer such as
+        _lib.gather_rows_split can write the minibatch straight into them and then call step(None, t, n=n)."""
+        self._reserve(max(n, 1))
+        return self.Xhi[:n], self.Xlo[:n]
+
+    def step(self, Xt: Optional[torch.Tensor], t: float, codes: Optional[torch.Tensor] = None, n: Optional[int] = None):
         """One minibatch: Xt (n_local x d) are THIS rank's columns of the minibatch, t the step index
-        (w = t^-beta).  Returns the local codes Ht (view, valid until the next call)."""
+        (w = t^-beta).  Returns the local codes Ht (view, valid until the next call).
+        Xt=None (tensor-core path only): the minibatch is already in split_buffers(n)."""
         main, side = self.main, self.side
-        n = Xt.shape[0]
+        presplit = Xt is None
+        if presplit and not self.use_tc:
+            raise _lib.OnmfKernelError("step(None, ...) needs the tensor-core path")
+        n = Xt.shape[0] if not presplit else int(n)
         self._reserve(max(n, 1))
         w = float(t) ** (-self.beta)
         cur = self._cur
@@ -132,15 +160,32 @@ class OnmfEngine:
         if self.track_C:
             main.wait_stream(side)                  # P2 is single-buffered
         if n > 0:
+            if self.use_tc:
+                Xhi, Xlo = self.Xhi[:n], self.Xlo[:n]
+                if not presplit:
+                    _lib.split_tf32(Xt, Xhi, Xlo, stream=main)
+                    self.launches += 1
             if codes is None:
                 Ct = self.Ct[:n]
                 _lib.gram(self.W, self.G, stream=main)
-                _lib.cov(Xt, self.W, Ct, stream=main)
+                if self.use_tc:
+                    _lib.split_tf32(self.W, self.Whi, self.Wlo, stream=main)
+                    _lib.cov_tc(Xhi, Xlo, self.Whi, self.Wlo, Ct, stream=main)
+                    self.launches += 1
+                else:
+                    _lib.cov(Xt, self.W, Ct, stream=main)
                 _lib.lasso_lars(self.G, Ct, self.d, self.alpha, Ht, self._ws_lars, max_iter=self.max_iter,
                                 stats=self._stats_ptr(), stream=main)
-            _lib.surrogate_partial(Ht, Xt, self.P[cur], self._ws_sur, stream=main)
+            if self.use_tc:
+                _lib.split_tf32(Ht, self.Hhi[:n], self.Hlo[:n], stream=main)
+                _lib.surrogate_partial_tc(self.Hhi[:n], self.Hlo[:n], Xhi, Xlo, self.P[cur], self._ws_sur, stream=main)
+                self.launches += 2
+            else:
+                _lib.surrogate_partial(Ht, Xt, self.P[cur], self._ws_sur, stream=main)
             self.launches += 7
             if self.track_C:
+                if presplit:
+                    raise _lib.OnmfKernelError("track_C needs the unsplit minibatch")
                 _lib.xxt_partial(Xt, self.P2, self._ws_sur, stream=main)
                 self.launches += 2
         else:
