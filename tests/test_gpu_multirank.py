@@ -1,0 +1,65 @@
+"""N>1 on the GPU: two ranks (gloo process group over CUDA tensors, both on cuda:0 -- NCCL refuses two ranks on
+one device) shard a minibatch by columns, all-reduce the packed partial sums inside OnmfEngine.step, and must
+end with the same W, A, B as a single rank that saw the whole minibatch (up to fp32 summation order), and with
+bit-identical state on both ranks."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from onmf_ontf_ndl_b200 import OnmfEngine
+    from onmf_ontf_ndl_b200.parallel import shard_range
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(0)
+    d, k, n = 64, 32, 1001                       # TC-eligible shape, ragged shard sizes
+    X = torch.from_numpy(rng.random((n, d)).astype(np.float32)).to(dev)
+    W0 = rng.random((d, k))
+    res = {}
+    for dt in (torch.float32, torch.float64):
+        eng = OnmfEngine(d, k, alpha=0.5, dtype=dt, device=dev, process_group=dist.group.WORLD)
+        eng.set_state(W0)
+        lo, hi = shard_range(n, world, rank)
+        Xs = X[lo:hi].to(dt).contiguous()
+        for t in (1, 2, 3, 4):
+            eng.step(Xs, float(t))
+        W, A, B, _ = eng.state()
+        torch.cuda.synchronize()
+        gathered = [torch.zeros_like(W.cpu()) for _ in range(world)]
+        dist.all_gather(gathered, W.cpu())
+        same = all(torch.equal(gathered[0], g) for g in gathered)
+        if rank == 0:
+            ref = OnmfEngine(d, k, alpha=0.5, dtype=dt, device=dev)
+            ref.set_state(W0)
+            Xf = X.to(dt).contiguous()
+            for t in (1, 2, 3, 4):
+                ref.step(Xf, float(t))
+            Wr, Ar, Br, _ = ref.state()
+            torch.cuda.synchronize()
+            tol = 1e-11 if dt == torch.float64 else 2e-4
+            ok = (float((W - Wr).abs().max()) <= tol * float(Wr.abs().max()) and
+                  float((A - Ar).abs().max()) <= tol * float(Ar.abs().max()) and
+                  float((B - Br).abs().max()) <= tol * float(Br.abs().max()))
+            res[str(dt)] = bool(ok and same)
+        else:
+            res[str(dt)] = bool(same)
+    out[rank] = all(res.values())
+    dist.destroy_process_group()
+
+
+def test_two_ranks_match_single_rank():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_run, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]

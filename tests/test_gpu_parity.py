@@ -331,3 +331,53 @@ def test_empty_minibatch_and_loud_failures():
         _lib.gram(torch.rand(4, 3), torch.empty(3, 3))               # CPU tensors are refused, not silently handled
     with pytest.raises(_lib.OnmfKernelError):
         OnmfEngine(10, 600, device=dev()).sparse_code(torch.rand(4, 10, device=dev()))   # k > 512 unsupported
+
+
+# ---------------------------------------------------------------------------------------------- tensor-core path
+@pytest.mark.parametrize("n,d,k", [(256, 64, 64), (300, 128, 96), (1000, 400, 100), (4096, 1024, 256), (513, 300, 52), (33, 32, 32)])
+def test_tensor_core_gemms_vs_fp64(n, d, k):
+    """tcgen05 3xTF32 products against float64; tolerance 2e-5 = the round-toward-zero accumulation bias of the
+    tensor core over the capped 32-K-block chain, far below the 1.5e-3 of plain TF32."""
+    g = torch.Generator(device=dev()); g.manual_seed(n + d + k)
+    X = torch.rand(n, d, device=dev(), generator=g); W = torch.rand(d, k, device=dev(), generator=g)
+    H = torch.rand(n, k, device=dev(), generator=g) * (torch.rand(n, k, device=dev(), generator=g) < 0.2)
+    assert _lib.tc_supported(k, d)
+    def split(x):
+        hi, lo = torch.empty_like(x), torch.empty_like(x)
+        _lib.split_tf32(x, hi, lo)
+        return hi, lo
+    Xh, Xl = split(X); Wh, Wl = split(W); Hh, Hl = split(H)
+    assert torch.equal(Xh + Xl, X)                                   # the split is exact
+    assert torch.equal(Xh.view(torch.int32) & 0x1FFF, torch.zeros_like(Xh, dtype=torch.int32))   # hi is a TF32 number
+    Ct = torch.full((n, k), float("nan"), device=dev())
+    _lib.cov_tc(Xh, Xl, Wh, Wl, Ct)
+    P = torch.full((k, k + d), float("nan"), device=dev())
+    ws = torch.empty(_lib.surrogate_tc_workspace(n, k, d), dtype=torch.uint8, device=dev())
+    _lib.surrogate_partial_tc(Hh, Hl, Xh, Xl, P, ws)
+    P2 = torch.empty_like(P); _lib.surrogate_partial_tc(Hh, Hl, Xh, Xl, P2, ws)
+    assert torch.equal(P, P2)                                        # deterministic split-K
+    Xd, Wd, Hd = X.double(), W.double(), H.double()
+    relt = lambda a, b: float((a.double() - b).norm() / b.norm())
+    assert relt(Ct, Xd @ Wd) < 2e-5 and relt(P[:, :k], Hd.T @ Hd) < 2e-5 and relt(P[:, k:], Hd.T @ Xd) < 2e-5
+
+
+def test_tensor_core_and_cuda_core_paths_agree_end_to_end(golden_dir):
+    """same online run with and without the tensor-core GEMMs: dictionaries agree far inside the fp32 bar."""
+    g = load(golden_dir, "cfg4_ising_pm1")
+    X, W0 = g["X"], g["W0"]
+    outs = []
+    for use_tc in (True, False):
+        eng = OnmfEngine(400, 100, alpha=1.0, dtype=torch.float32, device=dev(), use_tc=use_tc)
+        assert eng.use_tc == use_tc
+        eng.set_state(W0)
+        pool = tt(X.T, torch.float32)
+        for i in range(int(g["n_steps"])):
+            idx = torch.from_numpy(g["idx"][i].astype(np.int64)).to(dev())
+            Xb = torch.empty(len(idx), 400, dtype=torch.float32, device=dev())
+            _lib.gather_rows(pool, idx, Xb)
+            eng.step(Xb, float(i + 1))
+        W, A, B, _ = eng.state()
+        torch.cuda.synchronize()
+        outs.append(W.cpu().numpy().astype(np.float64))
+        assert per_atom(outs[-1], g["W_final"]) < ATOM_TOL_FP32
+    assert per_atom(outs[0], outs[1]) < 2e-4
