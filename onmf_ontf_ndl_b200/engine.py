@@ -49,7 +49,9 @@ class OnmfEngine:
         self.A = torch.zeros(k, k, dtype=dt_, device=dev)
         self.B = torch.zeros(k, d, dtype=dt_, device=dev)
         self.C = torch.zeros(d, d, dtype=dt_, device=dev) if track_C else None
-        self.G = torch.empty(k, k, dtype=dt_, device=dev)
+        self.G = torch.empty(k, k, dtype=dt_, device=dev)          # Gram of self.W (kept in step with it)
+        self.G_next = torch.empty(k, k, dtype=dt_, device=dev)
+        self._G_scratch = torch.empty(k, k, dtype=dt_, device=dev)  # for sparse_code() against a foreign W
         self.P = [torch.zeros(k, k + d, dtype=dt_, device=dev) for _ in range(2)]
         self.P2 = torch.zeros(d, d, dtype=dt_, device=dev) if track_C else None
         self._cap = 0
@@ -59,6 +61,10 @@ class OnmfEngine:
         if self.use_tc:
             self.Whi = torch.empty(d, k, dtype=dt_, device=dev)
             self.Wlo = torch.empty(d, k, dtype=dt_, device=dev)
+            self.Whi_next = torch.empty(d, k, dtype=dt_, device=dev)
+            self.Wlo_next = torch.empty(d, k, dtype=dt_, device=dev)
+            self._Whi_s = torch.empty(d, k, dtype=dt_, device=dev)
+            self._Wlo_s = torch.empty(d, k, dtype=dt_, device=dev)
         self.Xhi = self.Xlo = self.Hhi = self.Hlo = None
         self.stats = torch.zeros(len(_lib.STATS_FIELDS), dtype=torch.int64, device=dev) if collect_stats else None
         self.main = torch.cuda.current_stream(dev)
@@ -80,6 +86,16 @@ class OnmfEngine:
                 dst.zero_()
             else:
                 dst.copy_(torch.as_tensor(src).to(self.device, self.dtype))
+        self._derive(self.W, self.G, getattr(self, "Whi", None), getattr(self, "Wlo", None), self.main)
+
+    def _derive(self, W, G, Whi, Wlo, stream):
+        """Everything the coder needs that depends on the dictionary only: Gram matrix and (tensor-core path)
+        the TF32 hi/lo split of W.  Runs right after the dictionary update, off the minibatch's critical path."""
+        _lib.gram(W, G, stream=stream)
+        self.launches += 1
+        if self.use_tc:
+            _lib.split_tf32(W, Whi, Wlo, stream=stream)
+            self.launches += 1
 
     def _reserve(self, n):
         if n <= self._cap:
@@ -108,20 +124,26 @@ class OnmfEngine:
         """Ht (n x k) = positive lasso_lars codes of the rows of Xt (n x d) against W (default: current)."""
         n = Xt.shape[0]
         self._reserve(n)
-        W = self.W if W is None else W
         Ct = self.Ct[:n]
         Ht = self.Ht[:n] if out is None else out
-        _lib.gram(W, self.G)
+        if W is None:
+            self.flush()
+            W, G = self.W, self.G
+            Whi, Wlo = (self.Whi, self.Wlo) if self.use_tc else (None, None)
+        else:
+            G = self._G_scratch
+            Whi, Wlo = (self._Whi_s, self._Wlo_s) if self.use_tc else (None, None)
+            self._derive(W, G, Whi, Wlo, torch.cuda.current_stream(self.device))
         if self.use_tc and n > 0:
             _lib.split_tf32(Xt, self.Xhi[:n], self.Xlo[:n])
-            _lib.split_tf32(W, self.Whi, self.Wlo)
-            _lib.cov_tc(self.Xhi[:n], self.Xlo[:n], self.Whi, self.Wlo, Ct)
+            _lib.cov_tc(self.Xhi[:n], self.Xlo[:n], Whi, Wlo, Ct)
             self.launches += 2
         else:
             _lib.cov(Xt, W, Ct)
-        _lib.lasso_lars(self.G, Ct, self.d, self.alpha if alpha is None else alpha, Ht, self._ws_lars,
+            self.launches += 1
+        _lib.lasso_lars(G, Ct, self.d, self.alpha if alpha is None else alpha, Ht, self._ws_lars,
                         max_iter=self.max_iter, stats=self._stats_ptr())
-        self.launches += 4
+        self.launches += 5
         return Ht
 
     # ------------------------------------------------------------------ one online step
@@ -153,6 +175,7 @@ class OnmfEngine:
         with torch.cuda.stream(side):
             side.wait_event(self._ev_code)
             _lib.update_dict(self.W, self.A, self.B, self.W_next, stream=side)
+            self._derive(self.W_next, self.G_next, getattr(self, "Whi_next", None), getattr(self, "Wlo_next", None), side)
             self._ev_W.record(side)
             self.launches += 1
         # main stream: code this minibatch with W_{t-1}
@@ -167,11 +190,8 @@ class OnmfEngine:
                     self.launches += 1
             if codes is None:
                 Ct = self.Ct[:n]
-                _lib.gram(self.W, self.G, stream=main)
                 if self.use_tc:
-                    _lib.split_tf32(self.W, self.Whi, self.Wlo, stream=main)
                     _lib.cov_tc(Xhi, Xlo, self.Whi, self.Wlo, Ct, stream=main)
-                    self.launches += 1
                 else:
                     _lib.cov(Xt, self.W, Ct, stream=main)
                 _lib.lasso_lars(self.G, Ct, self.d, self.alpha, Ht, self._ws_lars, max_iter=self.max_iter,
@@ -182,7 +202,7 @@ class OnmfEngine:
                 self.launches += 2
             else:
                 _lib.surrogate_partial(Ht, Xt, self.P[cur], self._ws_sur, stream=main)
-            self.launches += 7
+            self.launches += 8 if codes is None else 3
             if self.track_C:
                 if presplit:
                     raise _lib.OnmfKernelError("track_C needs the unsplit minibatch")
@@ -213,6 +233,10 @@ class OnmfEngine:
         # the next coding needs W_t (= W_next): wait for the dictionary update only
         main.wait_event(self._ev_W)
         self.W, self.W_next = self.W_next, self.W
+        self.G, self.G_next = self.G_next, self.G
+        if self.use_tc:
+            self.Whi, self.Whi_next = self.Whi_next, self.Whi
+            self.Wlo, self.Wlo_next = self.Wlo_next, self.Wlo
         self._cur ^= 1
         return Ht
 
