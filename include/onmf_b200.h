@@ -103,6 +103,15 @@ size_t onmf_lasso_lars_workspace(int dtype, int k, int64_t n);
 int onmf_lasso_lars(int dtype, const void* G, const void* Ct, int64_t n, int k, int d, double alpha,
                     int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
                     onmf_lars_stats* stats, void* stream);
+/* same, with explicit tier scheduling.  Columns whose active set outgrows a tier's slot count are re-walked from the
+ * start by the next (larger, lower-occupancy) tier.  first_tier = 0 / 1 starts every column in that tier;
+ * first_tier = -1 (what onmf_lasso_lars uses) is adaptive: a device-side flag kept in the first 64 bytes of the
+ * workspace remembers whether more than 1/16 of the previous call's columns needed the larger tier.  The workspace
+ * must therefore be zero-filled once before its first use and may be reused across calls.  Results are identical
+ * for every setting. */
+int onmf_lasso_lars_ex(int dtype, const void* G, const void* Ct, int64_t n, int k, int d, double alpha,
+                       int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
+                       onmf_lars_stats* stats, int first_tier, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  surrogate aggregation

@@ -42,6 +42,7 @@ SIGNATURES = {
     "onmf_cov": (_i, [_i, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "onmf_lasso_lars_workspace": (_sz, [_i, _i, _i64]),
     "onmf_lasso_lars": (_i, [_i, _vp, _vp, _i64, _i, _i, _dbl, _i, _vp, _vp, _sz, _vp, _vp]),
+    "onmf_lasso_lars_ex": (_i, [_i, _vp, _vp, _i64, _i, _i, _dbl, _i, _vp, _vp, _sz, _vp, _i, _vp]),
     "onmf_surrogate_workspace": (_sz, [_i, _i64, _i, _i]),
     "onmf_surrogate_partial": (_i, [_i, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _vp]),
     "onmf_surrogate_blend": (_i, [_i, _vp, _i, _i, _dbl, _vp, _vp, _vp]),
@@ -156,11 +157,12 @@ def lasso_lars_workspace(dtype, k, n):
     return int(load().onmf_lasso_lars_workspace(F64 if dtype == torch.float64 else F32, k, n))
 
 
-def lasso_lars(G, Ct, d, alpha, Ht, workspace, max_iter=1000, stats=None, stream=None):
+def lasso_lars(G, Ct, d, alpha, Ht, workspace, max_iter=1000, stats=None, stream=None, first_tier=-1):
     _req(G, "G"); _req(Ct, "Ct", G.dtype); _req(Ht, "Ht", G.dtype); _req(workspace, "workspace", torch.uint8)
     n, k = Ct.shape
-    _check(load().onmf_lasso_lars(dt(G), _ptr(G), _ptr(Ct), n, k, d, float(alpha), int(max_iter), _ptr(Ht),
-                                  _ptr(workspace), workspace.numel(), _ptr(stats), _stream(stream)), "onmf_lasso_lars")
+    _check(load().onmf_lasso_lars_ex(dt(G), _ptr(G), _ptr(Ct), n, k, d, float(alpha), int(max_iter), _ptr(Ht),
+                                     _ptr(workspace), workspace.numel(), _ptr(stats), int(first_tier), _stream(stream)),
+           "onmf_lasso_lars")
     return Ht
 
 

@@ -54,6 +54,10 @@ struct LarsParams {
   double* Mscratch;                  // last tier: per-group M storage in global memory
   onmf_lars_stats* stats;
   int count_stats;                   // 1 on the first tier (overflow columns are counted once)
+  unsigned int* over_thresh;         // counts finished columns whose active set exceeded `thresh` (scheduling feedback)
+  int thresh;
+  const unsigned int* hint;          // device-side scheduling state: the kernel runs only if *hint == run_if
+  int run_if;
 };
 
 template <typename T> struct Num;
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
   constexpr int UQ = (NA >= 16 || sizeof(T) == 8) ? 2 : 4;  // Gram rows in flight per correlation-pass batch
   static_assert(NA % VEC == 0 && SMAX % 4 == 0, "bad tile shape");
 
+  if (P.hint != nullptr && *P.hint != (unsigned)P.run_if) return;   // the other first-tier variant handles this call
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = P.k;
   T* Gs = reinterpret_cast<T*>(smem_raw);
@@ -706,6 +711,7 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
       } else {
         ++st_cols;
         if (status & ~8) ++st_flag;
+        if (P.over_thresh != nullptr && max_act > P.thresh) atomicAdd(P.over_thresh, 1u);
       }
       st_maxact = max_act > st_maxact ? max_act : st_maxact;
     }
@@ -731,11 +737,21 @@ __global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
 // ------------------------------------------------------------------------------------------------
 
 struct LarsWs {           // header at the start of the caller's workspace
-  unsigned long long ticket[4];
-  unsigned int ovf_count[4];
-  unsigned int pad[4];
+  unsigned long long ticket[5];   // per launch work counters                 (reset every call)
+  unsigned int ovf_count[4];      // per tier overflow list lengths           (reset every call)
+  unsigned int over_thresh;       // columns that needed more than tier-0 slots while run in tier 1 (reset every call)
+  unsigned int hint;              // PERSISTS across calls: 0 = start columns in tier 0, 1 = start them in tier 1
 };
 static_assert(sizeof(LarsWs) == 64, "header size");
+constexpr size_t LARS_WS_RESET_BYTES = 60;
+
+// device-side scheduling feedback: columns that outgrow tier 0 are re-walked from the start by tier 1, so when more
+// than 1/16 of a call's columns did (or would have), the next call starts every column in tier 1 directly.
+__global__ void update_hint_kernel(LarsWs* hdr, long long n) {
+  const unsigned int cur = hdr->hint;
+  const unsigned long long big = cur == 0 ? hdr->ovf_count[0] : hdr->over_thresh;
+  hdr->hint = (big * 16ull > (unsigned long long)n) ? 1u : 0u;
+}
 
 static int k_class(int k) { return k <= 32 ? 0 : k <= 64 ? 1 : k <= 128 ? 2 : k <= 256 ? 3 : k <= 512 ? 4 : -1; }
 static int class_kp(int c) { static const int kp[5] = {32, 64, 128, 256, 512}; return kp[c]; }
@@ -793,7 +809,7 @@ static size_t ws_gp_bytes(int k, int kp) { return round_up<size_t>((size_t)k * k
 // tiers: S0 slots, then S1, S2, S3 (0 = none); the last non-zero tier keeps M in global scratch when GL
 template <typename T, int LPC, int NA, int S0, int S1, int S2, int S3, bool GL>
 static int launch_class(const T* G, const T* Ct, long long n, int k, int d, double alpha, int max_iter, T* Ht,
-                        unsigned char* ws, onmf_lars_stats* stats, cudaStream_t st) {
+                        unsigned char* ws, onmf_lars_stats* stats, int first_tier, cudaStream_t st) {
   constexpr int KP = LPC * NA;
   LarsWs* hdr = reinterpret_cast<LarsWs*>(ws);
   const size_t lb = ws_list_bytes(n);
@@ -801,7 +817,7 @@ static int launch_class(const T* G, const T* Ct, long long n, int k, int d, doub
                          reinterpret_cast<long long*>(ws + sizeof(LarsWs) + lb)};
   T* gp = reinterpret_cast<T*>(ws + sizeof(LarsWs) + 2 * lb);
   double* mscr = reinterpret_cast<double*>(ws + sizeof(LarsWs) + 2 * lb + ws_gp_bytes(k, KP));
-  ONMF_CUDA(cudaMemsetAsync(hdr, 0, sizeof(LarsWs), st));
+  ONMF_CUDA(cudaMemsetAsync(hdr, 0, LARS_WS_RESET_BYTES, st));   // everything but the persistent hint
   pad_gram_kernel<T><<<cdiv(k * KP, 256), 256, 0, st>>>(G, k, KP, gp);
   ONMF_LAUNCH_CHECK("pad_gram_kernel");
 
@@ -809,45 +825,66 @@ static int launch_class(const T* G, const T* Ct, long long n, int k, int d, doub
   P.G = G; P.Gp = gp; P.Ct = Ct; P.Ht = Ht; P.n = n; P.k = k; P.d = d; P.max_iter = max_iter;
   P.amin = T(alpha) / T(d);
   P.Mscratch = nullptr; P.stats = stats;
-  // tier t reads list (t-1)&1 and appends to list t&1
-  auto tier_params = [&](int t, bool has_next, bool glob) {
+  // tier t reads list (t-1)&1 and appends to list t&1.  first_tier: 0 / 1 = start every column in that tier,
+  // -1 = adaptive (both first-tier variants are launched, the device-side hint decides which one does the work).
+  const bool adaptive = (first_tier < 0) && S1 > 0;
+  const int first = (first_tier > 0 && S1 > 0) ? 1 : 0;
+  P.over_thresh = nullptr; P.thresh = S0; P.hint = nullptr; P.run_if = 0;
+  auto tier_params = [&](int t, int ticket, bool from_list, bool has_next, bool glob) {
     LarsParams<T> Q = P;
-    Q.ticket = &hdr->ticket[t];
-    Q.col_list = t ? lists[(t - 1) & 1] : nullptr;
-    Q.n_list = t ? &hdr->ovf_count[t - 1] : nullptr;
+    Q.ticket = &hdr->ticket[ticket];
+    Q.col_list = from_list ? lists[(t - 1) & 1] : nullptr;
+    Q.n_list = from_list ? &hdr->ovf_count[t - 1] : nullptr;
     Q.ovf_list = has_next ? lists[t & 1] : nullptr;
     Q.ovf_count = &hdr->ovf_count[t];
     Q.Mscratch = glob ? mscr : nullptr;
-    Q.count_stats = t == 0;
+    Q.count_stats = !from_list;
     return Q;
   };
-  int rc = launch_tier<T, LPC, NA, S0, (GL && S1 == 0)>(tier_params(0, S1 > 0, GL && S1 == 0), n, 16, st);
-  if (rc) return rc;
-  if constexpr (S1 > 0) {
-    rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(tier_params(1, S2 > 0, GL && S2 == 0), n, (GL && S2 == 0) ? 2 : 16, st);
+  int rc = ONMF_OK;
+  if (adaptive || first == 0) {
+    LarsParams<T> Q = tier_params(0, 0, false, S1 > 0, GL && S1 == 0);
+    if (adaptive) { Q.hint = &hdr->hint; Q.run_if = 0; }
+    rc = launch_tier<T, LPC, NA, S0, (GL && S1 == 0)>(Q, n, 16, st);
     if (rc) return rc;
   }
+  if constexpr (S1 > 0) {
+    if (adaptive || first == 1) {      // tier 1 over ALL columns
+      LarsParams<T> Q = tier_params(1, 4, false, S2 > 0, GL && S2 == 0);
+      if (adaptive) { Q.hint = &hdr->hint; Q.run_if = 1; Q.over_thresh = &hdr->over_thresh; }
+      rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(Q, n, (GL && S2 == 0) ? 2 : 16, st);
+      if (rc) return rc;
+    }
+    if (adaptive || first == 0) {      // tier 1 over tier 0's overflow list
+      rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(tier_params(1, 1, true, S2 > 0, GL && S2 == 0), n, (GL && S2 == 0) ? 2 : 16, st);
+      if (rc) return rc;
+    }
+  }
   if constexpr (S2 > 0) {
-    rc = launch_tier<T, LPC, NA, S2, (GL && S3 == 0)>(tier_params(2, S3 > 0, GL && S3 == 0), n, (GL && S3 == 0) ? 2 : 16, st);
+    rc = launch_tier<T, LPC, NA, S2, (GL && S3 == 0)>(tier_params(2, 2, true, S3 > 0, GL && S3 == 0), n, (GL && S3 == 0) ? 2 : 16, st);
     if (rc) return rc;
   }
   if constexpr (S3 > 0) {
-    rc = launch_tier<T, LPC, NA, S3, GL>(tier_params(3, false, GL), n, GL ? 2 : 16, st);
+    rc = launch_tier<T, LPC, NA, S3, GL>(tier_params(3, 3, true, false, GL), n, GL ? 2 : 16, st);
     if (rc) return rc;
+  }
+  if (adaptive) {
+    update_hint_kernel<<<1, 1, 0, st>>>(hdr, n);
+    ONMF_LAUNCH_CHECK("update_hint_kernel");
   }
   return ONMF_OK;
 }
 
 template <typename T>
 static int lasso_lars_t(const void* G, const void* Ct, long long n, int k, int d, double alpha, int max_iter,
-                        void* Ht, void* ws, onmf_lars_stats* stats, cudaStream_t st) {
+                        void* Ht, void* ws, onmf_lars_stats* stats, int first_tier, cudaStream_t st) {
   const T* g = (const T*)G; const T* c = (const T*)Ct; T* h = (T*)Ht; unsigned char* w = (unsigned char*)ws;
   switch (k_class(k)) {
-    case 0: return launch_class<T, 8, 4, 32, 0, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 1: return launch_class<T, 16, 4, 32, 64, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 2: return launch_class<T, 32, 4, 32, 64, 128, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 3: return launch_class<T, 32, 8, 40, 64, 128, 256, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
-    case 4: return launch_class<T, 32, 16, 40, 64, 128, 512, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, st);
+    case 0: return launch_class<T, 8, 4, 32, 0, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+    case 1: return launch_class<T, 16, 4, 32, 64, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+    case 2: return launch_class<T, 32, 4, 32, 64, 128, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+    case 3: return launch_class<T, 32, 8, 40, 64, 128, 256, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+    case 4: return launch_class<T, 32, 16, 40, 64, 128, 512, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
   }
   return fail(ONMF_E_UNSUPPORTED, "lasso_lars: n_components > 512 not instantiated");
 }
@@ -864,9 +901,9 @@ extern "C" size_t onmf_lasso_lars_workspace(int dtype, int k, int64_t n) {
   return bytes + 256;
 }
 
-extern "C" int onmf_lasso_lars(int dtype, const void* G, const void* Ct, int64_t n, int k, int d, double alpha,
-                               int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
-                               onmf_lars_stats* stats, void* stream) {
+extern "C" int onmf_lasso_lars_ex(int dtype, const void* G, const void* Ct, int64_t n, int k, int d, double alpha,
+                                  int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
+                                  onmf_lars_stats* stats, int first_tier, void* stream) {
   using namespace onmf;
   if (!G || !Ct || !Ht || !workspace) return fail(ONMF_E_ARG, "lasso_lars: null pointer");
   if (n < 0 || k <= 0 || d <= 0 || max_iter < 0 || !(alpha >= 0.0)) return fail(ONMF_E_ARG, "lasso_lars: bad size/alpha");
@@ -875,6 +912,12 @@ extern "C" int onmf_lasso_lars(int dtype, const void* G, const void* Ct, int64_t
   if (workspace_bytes < onmf_lasso_lars_workspace(dtype, k, n)) return fail(ONMF_E_WORKSPACE, "lasso_lars: workspace too small");
   if ((uintptr_t)workspace % 256) return fail(ONMF_E_ARG, "lasso_lars: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == ONMF_F32) return lasso_lars_t<float>(G, Ct, n, k, d, alpha, max_iter, Ht, workspace, stats, st);
-  return lasso_lars_t<double>(G, Ct, n, k, d, alpha, max_iter, Ht, workspace, stats, st);
+  if (dtype == ONMF_F32) return lasso_lars_t<float>(G, Ct, n, k, d, alpha, max_iter, Ht, workspace, stats, first_tier, st);
+  return lasso_lars_t<double>(G, Ct, n, k, d, alpha, max_iter, Ht, workspace, stats, first_tier, st);
+}
+
+extern "C" int onmf_lasso_lars(int dtype, const void* G, const void* Ct, int64_t n, int k, int d, double alpha,
+                               int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
+                               onmf_lars_stats* stats, void* stream) {
+  return onmf_lasso_lars_ex(dtype, G, Ct, n, k, d, alpha, max_iter, Ht, workspace, workspace_bytes, stats, -1, stream);
 }

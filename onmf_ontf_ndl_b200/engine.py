@@ -66,7 +66,8 @@ class OnmfEngine:
             self._Whi_s = torch.empty(d, k, dtype=dt_, device=dev)
             self._Wlo_s = torch.empty(d, k, dtype=dt_, device=dev)
         self.Xhi = self.Xlo = self.Hhi = self.Hlo = None
-        self.stats = torch.zeros(len(_lib.STATS_FIELDS), dtype=torch.int64, device=dev) if collect_stats else None
+        self.stats = torch.zeros(len(_lib.STATS_FIELDS), dtype=torch.int64, device=dev)   # in-kernel work counters
+        self._collect = bool(collect_stats)
         self.main = torch.cuda.current_stream(dev)
         self.side = torch.cuda.Stream(dev)
         self._ev_P = torch.cuda.Event()        # P[cur] complete on main
@@ -104,7 +105,7 @@ class OnmfEngine:
         self._cap = int(n)
         self.Ct = torch.empty(self._cap, self.k, dtype=dt_, device=dev)
         self.Ht = torch.empty(self._cap, self.k, dtype=dt_, device=dev)
-        self._ws_lars = torch.empty(_lib.lasso_lars_workspace(dt_, self.k, self._cap), dtype=torch.uint8, device=dev)
+        self._ws_lars = torch.zeros(_lib.lasso_lars_workspace(dt_, self.k, self._cap), dtype=torch.uint8, device=dev)
         nbytes = _lib.surrogate_workspace(dt_, self._cap, self.k, self.d)
         if self.track_C:
             nbytes = max(nbytes, 64 * self.d * self.d * self.W.element_size() + 256)
@@ -117,7 +118,7 @@ class OnmfEngine:
         self._ws_sur = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
     def _stats_ptr(self):
-        return self.stats if self.stats is not None else None
+        return self.stats
 
     # ------------------------------------------------------------------ coding only
     def sparse_code(self, Xt: torch.Tensor, W: Optional[torch.Tensor] = None, alpha=None, out=None):
@@ -281,8 +282,6 @@ class OnmfEngine:
         return self.W, self.A, self.B, self.C
 
     def read_stats(self):
-        if self.stats is None:
-            return None
         torch.cuda.synchronize(self.device)
         vals = self.stats.cpu().tolist()
         return dict(zip(_lib.STATS_FIELDS, vals))
