@@ -168,6 +168,19 @@ int onmf_update_dict(int dtype, const void* W_in, const void* A, const void* B, 
 int onmf_pgd_sweep(int dtype, const void* G, const void* Ct, int64_t n, int k, double alpha,
                    int it, void* Ht, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * batched reconstruction: replaces the per-patch Python loop
+ * image_reconstruction.py:375-392 (one update_code_within_radius call + k*k python paints per patch)
+ * ------------------------------------------------------------------------------------------- */
+/* the complete projected-gradient coder per sample (outer loop + per-sample stopping test in-kernel), i.e. what the
+ * reference computes when it calls update_code_within_radius on ONE patch at a time; Ht (n x k) holds H0 on entry */
+int onmf_pgd_code_columns(int dtype, const void* G, const void* Ct, int64_t n, int k, double alpha, int sub_iter,
+                          double stopping_diff, void* Ht, void* stream);
+/* overlap-averaged canvas (H x W x C) from the reconstructions R ((ny*nx) x ldr) of the p x p patches whose top-left
+ * corners lie on the grid (gy*stride, gx*stride); count (H x W, may be NULL) receives the overlap counts */
+int onmf_patch_grid_mean(int dtype, const void* R, int64_t ldr, int ny, int nx, int p, int stride, int C, int H,
+                         int W, void* canvas, void* count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

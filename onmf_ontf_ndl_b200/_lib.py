@@ -56,6 +56,8 @@ SIGNATURES = {
     "onmf_surrogate_partial_tc": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _vp]),
     "onmf_update_dict": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "onmf_pgd_sweep": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _vp, _vp]),
+    "onmf_pgd_code_columns": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _dbl, _vp, _vp]),
+    "onmf_patch_grid_mean": (_i, [_i, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -254,3 +256,22 @@ def surrogate_partial_tc(Hhi, Hlo, Xhi, Xlo, P, workspace, stream=None):
     _check(load().onmf_surrogate_partial_tc(_ptr(Hhi), _ptr(Hlo), _ptr(Xhi), _ptr(Xlo), n, k, d, _ptr(P), _ptr(workspace),
                                             workspace.numel(), _stream(stream)), "onmf_surrogate_partial_tc")
     return P
+
+
+# ---- batched reconstruction ---------------------------------------------------------------------
+
+def pgd_code_columns(G, Ct, alpha, sub_iter, stopping_diff, Ht, stream=None):
+    _req(G, "G"); _req(Ct, "Ct", G.dtype); _req(Ht, "Ht", G.dtype)
+    n, k = Ct.shape
+    _check(load().onmf_pgd_code_columns(dt(G), _ptr(G), _ptr(Ct), n, k, float(alpha), int(sub_iter), float(stopping_diff),
+                                        _ptr(Ht), _stream(stream)), "onmf_pgd_code_columns")
+    return Ht
+
+
+def patch_grid_mean(R, ny, nx, p, stride, C, H, W, canvas, count=None, stream=None):
+    _req(R, "R"); _req(canvas, "canvas", R.dtype)
+    if count is not None:
+        _req(count, "count", R.dtype)
+    _check(load().onmf_patch_grid_mean(dt(R), _ptr(R), R.stride(0), ny, nx, p, stride, C, H, W, _ptr(canvas), _ptr(count),
+                                       _stream(stream)), "onmf_patch_grid_mean")
+    return canvas

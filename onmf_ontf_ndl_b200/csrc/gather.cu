@@ -103,6 +103,117 @@ __global__ void pgd_sweep_kernel(const T* __restrict__ G, const T* __restrict__ 
   }
 }
 
+// The whole projected-gradient coder per sample, in-kernel: what the reference does when it codes ONE patch per call
+// (image_reconstruction.py:384: update_code_within_radius(patch, W, H0=None, r=None, alpha, sub_iter, stopping_diff)):
+// outer iterations i < sub_iter while dist > stopping_diff, dist = ||h - h_old||_2 / ||h_old||_2 (for a single column
+// the spectral norm of src/onmf.py:265 is the vector 2-norm).  One warp per sample; Ht holds H0 on entry.
+template <typename T, int NA>
+__global__ void pgd_columns_kernel(const T* __restrict__ G, const T* __restrict__ Ct, long long n, int k, T alpha, int sub_iter,
+                                   T stopping_diff, T* __restrict__ Ht) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Gs = reinterpret_cast<T*>(smem_raw);
+  for (int i = threadIdx.x; i < k * k; i += blockDim.x) Gs[i] = G[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long j = wid; j < n; j += nw) {
+    T h[NA], c[NA];
+#pragma unroll
+    for (int m = 0; m < NA; ++m) {
+      int i = lane + 32 * m;
+      h[m] = i < k ? Ht[(size_t)j * k + i] : T(0);
+      c[m] = i < k ? Ct[(size_t)j * k + i] : T(0);
+    }
+    T dist = T(1);
+    for (int it = 0; it < sub_iter && dist > stopping_diff; ++it) {
+      const T scale = (T)sqrt((double)it + 10.0);
+      T hold[NA];
+#pragma unroll
+      for (int m = 0; m < NA; ++m) hold[m] = h[m];
+      for (int q = 0; q < k; ++q) {
+        T part = T(0);
+#pragma unroll
+        for (int m = 0; m < NA; ++m) {
+          int i = lane + 32 * m;
+          if (i < k) part += Gs[q * k + i] * h[m];
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        T cq = T(0);
+#pragma unroll
+        for (int m = 0; m < NA; ++m)
+          if (lane + 32 * m == q) cq = c[m];
+        cq = __shfl_sync(0xffffffffu, cq, q & 31);
+        const T grad = part - cq + alpha;
+        const T step = T(1) / (scale * (Gs[q * k + q] + T(1)));
+#pragma unroll
+        for (int m = 0; m < NA; ++m)
+          if (lane + 32 * m == q) {
+            T v = h[m] - step * grad;
+            h[m] = v > T(0) ? v : T(0);
+          }
+      }
+      T num = T(0), den = T(0);
+#pragma unroll
+      for (int m = 0; m < NA; ++m) {
+        T dv = h[m] - hold[m];
+        num += dv * dv;
+        den += hold[m] * hold[m];
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        num += __shfl_xor_sync(0xffffffffu, num, off);
+        den += __shfl_xor_sync(0xffffffffu, den, off);
+      }
+      dist = sqrt(num) / sqrt(den);
+    }
+#pragma unroll
+    for (int m = 0; m < NA; ++m) {
+      int i = lane + 32 * m;
+      if (i < k) Ht[(size_t)j * k + i] = h[m];
+    }
+  }
+}
+
+// Overlap-averaged canvas from per-patch reconstructions (the running mean of image_reconstruction.py:389-392 and
+// sklearn's reconstruct_from_patches_2d): patches of size p x p (x C channels) with top-left corners on the grid
+// (gy*stride, gx*stride), gy < ny, gx < nx, stored row-major as R[(gy*nx + gx), (r*p + c)*C + ch].
+// Gather form: one thread per canvas element sums the covering patches in fixed order -> deterministic, no atomics.
+template <typename T>
+__global__ void patch_grid_mean_kernel(const T* __restrict__ R, long long ldr, int ny, int nx, int p, int stride, int C, int Hh,
+                                       int Ww, T* __restrict__ canvas, T* __restrict__ count) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long tot = (long long)Hh * Ww * C;
+  if (idx >= tot) return;
+  const int ch = (int)(idx % C);
+  const long long pix = idx / C;
+  const int x = (int)(pix % Ww), y = (int)(pix / Ww);
+  // grid rows gy with gy*stride <= y < gy*stride + p
+  int gy_hi = y / stride;
+  if (gy_hi > ny - 1) gy_hi = ny - 1;
+  int gy_lo = (y - p + stride) / stride;      // ceil((y - p + 1) / stride)
+  if (y - p + 1 <= 0) gy_lo = 0;
+  int gx_hi = x / stride;
+  if (gx_hi > nx - 1) gx_hi = nx - 1;
+  int gx_lo = (x - p + stride) / stride;
+  if (x - p + 1 <= 0) gx_lo = 0;
+  T acc = T(0);
+  int cnt = 0;
+  for (int gy = gy_lo; gy <= gy_hi; ++gy) {
+    const int r = y - gy * stride;
+    if (r < 0 || r >= p) continue;
+    for (int gx = gx_lo; gx <= gx_hi; ++gx) {
+      const int c = x - gx * stride;
+      if (c < 0 || c >= p) continue;
+      acc += R[(size_t)((long long)gy * nx + gx) * ldr + ((size_t)r * p + c) * C + ch];
+      ++cnt;
+    }
+  }
+  canvas[idx] = cnt > 0 ? acc / T(cnt) : T(0);
+  if (count != nullptr && ch == 0) count[pix] = T(cnt);
+}
+
 template <typename T>
 static int pgd_t(const T* G, const T* Ct, long long n, int k, double alpha, int it, T* Ht, cudaStream_t st) {
   size_t smem = (size_t)k * k * sizeof(T);
@@ -196,4 +307,51 @@ extern "C" int onmf_pgd_sweep(int dtype, const void* G, const void* Ct, int64_t 
   if (dtype == ONMF_F32) return pgd_t<float>((const float*)G, (const float*)Ct, n, k, alpha, it, (float*)Ht, st);
   if (dtype == ONMF_F64) return pgd_t<double>((const double*)G, (const double*)Ct, n, k, alpha, it, (double*)Ht, st);
   return fail(ONMF_E_ARG, "pgd_sweep: bad dtype");
+}
+
+extern "C" int onmf_pgd_code_columns(int dtype, const void* G, const void* Ct, int64_t n, int k, double alpha, int sub_iter,
+                                     double stopping_diff, void* Ht, void* stream) {
+  if (!G || !Ct || !Ht || n < 0 || k <= 0 || sub_iter < 0) return fail(ONMF_E_ARG, "pgd_code_columns: bad argument");
+  if (n == 0) return ONMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t tsz = dtype == ONMF_F64 ? 8 : 4;
+  size_t smem = (size_t)k * k * tsz;
+  if (smem > (size_t)max_smem_optin()) return fail(ONMF_E_UNSUPPORTED, "pgd_code_columns: Gram does not fit in shared memory");
+  int threads = 256;
+  int grid = (int)cdiv<long long>(n * 32, threads);
+  if (grid > 4 * num_sms()) grid = 4 * num_sms();
+#define ONMF_PGDC(TT, NA)                                                                              \
+  {                                                                                                    \
+    auto kern = pgd_columns_kernel<TT, NA>;                                                            \
+    ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    kern<<<grid, threads, smem, st>>>((const TT*)G, (const TT*)Ct, n, k, (TT)alpha, sub_iter, (TT)stopping_diff, (TT*)Ht); \
+  }
+#define ONMF_PGDC_K(TT)                                   \
+  if (k <= 32) ONMF_PGDC(TT, 1)                           \
+  else if (k <= 64) ONMF_PGDC(TT, 2)                      \
+  else if (k <= 128) ONMF_PGDC(TT, 4)                     \
+  else if (k <= 256) ONMF_PGDC(TT, 8)                     \
+  else if (k <= 512) ONMF_PGDC(TT, 16)                    \
+  else return fail(ONMF_E_UNSUPPORTED, "pgd_code_columns: n_components > 512");
+  if (dtype == ONMF_F32) { ONMF_PGDC_K(float) }
+  else if (dtype == ONMF_F64) { ONMF_PGDC_K(double) }
+  else return fail(ONMF_E_ARG, "pgd_code_columns: bad dtype");
+#undef ONMF_PGDC_K
+#undef ONMF_PGDC
+  ONMF_LAUNCH_CHECK("pgd_columns_kernel");
+  return ONMF_OK;
+}
+
+extern "C" int onmf_patch_grid_mean(int dtype, const void* R, int64_t ldr, int ny, int nx, int p, int stride, int C, int H, int W,
+                                    void* canvas, void* count, void* stream) {
+  if (!R || !canvas || ny <= 0 || nx <= 0 || p <= 0 || stride <= 0 || C <= 0 || H <= 0 || W <= 0 || ldr < (int64_t)p * p * C)
+    return fail(ONMF_E_ARG, "patch_grid_mean: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long tot = (long long)H * W * C;
+  unsigned grid = (unsigned)cdiv<long long>(tot, 256);
+  if (dtype == ONMF_F32) patch_grid_mean_kernel<float><<<grid, 256, 0, st>>>((const float*)R, ldr, ny, nx, p, stride, C, H, W, (float*)canvas, (float*)count);
+  else if (dtype == ONMF_F64) patch_grid_mean_kernel<double><<<grid, 256, 0, st>>>((const double*)R, ldr, ny, nx, p, stride, C, H, W, (double*)canvas, (double*)count);
+  else return fail(ONMF_E_ARG, "patch_grid_mean: bad dtype");
+  ONMF_LAUNCH_CHECK("patch_grid_mean_kernel");
+  return ONMF_OK;
 }

@@ -195,6 +195,20 @@ def main():
     Wn, aggn, coden = m.train_dict()
     np.savez_compressed(os.path.join(OUT, "shipped_onmf.npz"), X=Xs, seed=71, W=Wn, A=aggn[0],
                         B=aggn[1], code=coden, history_out=float(m.history))
+    # ---- reconstruction loop (image_reconstruction.py:358-406): the reference's own coder per patch, painting restated
+    imgr = _renoir(gray=False)[200:236, 150:190, :].copy()                 # 36 x 40 x 3 crop
+    np.random.seed(81)
+    Wr = np.random.rand(75, 25)
+    Wr /= np.linalg.norm(Wr, axis=0)
+    ny, nx = len(range(0, 36 - 5, 2)), len(range(0, 40 - 5, 2))
+    H0r = np.random.rand(ny * nx, 25).T                                    # same stream as one rand(r, 1) per patch
+    from oracle import onmf_oracle as O
+    rec, cnt, codes = O.reconstruct_image_loop(
+        imgr, Wr, 5, 2, 1, 10, 0.01, H0r,
+        coder=lambda patch, h0: onmf.update_code_within_radius(patch, Wr, H0=h0.copy(), r=None, alpha=1, sub_iter=10,
+                                                               stopping_diff=0.01))
+    np.savez_compressed(os.path.join(OUT, "reconstruct_color.npz"), img=imgr, W=Wr, H0=H0r, recons=rec, count=cnt,
+                        codes=codes, patch=5, stride=2)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-40s %8.1f KB" % (f, os.path.getsize(os.path.join(OUT, f)) / 1024))

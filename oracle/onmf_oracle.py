@@ -338,3 +338,37 @@ def gather_patches_color_tensor(img, coords, k):
 def surrogate_error(W, A, B, C):
     """tr(W A W^T) - 2 tr(W B) + tr(C)   (reference ising_reconstruction.py:133,164)."""
     return float(np.trace(W @ A @ W.T) - 2.0 * np.trace(W @ B) + np.trace(C))
+
+
+# --------------------------------------------------------------------------------------
+# patch-grid reconstruction loop (reference image_reconstruction.py:358-406)
+# --------------------------------------------------------------------------------------
+
+def reconstruct_image_loop(A, W, k, res, alpha, sub_iter, stopping_diff, H0, coder=None):
+    """for every grid patch (i, j), i in range(0, H-k, res), j in range(0, W-k, res): code the flattened patch (HWC order)
+    alone with update_code_within_radius(H0 = column of H0), reconstruct it with W and fold it into a running-mean canvas
+    (image_reconstruction.py:375-392).  `coder`: optional callable (patch_column) -> code column, e.g. the reference's
+    own update_code_within_radius.  Returns (canvas, overlap_count, codes (r x n))."""
+    A3 = A[:, :, None] if A.ndim == 2 else A
+    Hh, Ww, C = A3.shape
+    rec = np.zeros(A3.shape)
+    cnt = np.zeros((Hh, Ww))
+    codes = []
+    pidx = 0
+    for i in range(0, Hh - k, res):
+        for j in range(0, Ww - k, res):
+            patch = A3[i:i + k, j:j + k, :].reshape((-1, 1))
+            h0 = H0[:, pidx:pidx + 1]
+            if coder is None:
+                code = update_code_within_radius(patch, W, h0, r=None, alpha=alpha, sub_iter=sub_iter,
+                                                 stopping_diff=stopping_diff)
+            else:
+                code = coder(patch, h0)
+            codes.append(code[:, 0])
+            pr = (W @ code).T.reshape(k, k, C)
+            c = cnt[i:i + k, j:j + k]
+            rec[i:i + k, j:j + k, :] = (c[:, :, None] * rec[i:i + k, j:j + k, :] + pr) / (c[:, :, None] + 1)
+            cnt[i:i + k, j:j + k] += 1
+            pidx += 1
+    rec = rec[:, :, 0] if A.ndim == 2 else rec
+    return rec, cnt, (np.stack(codes, 1) if codes else np.zeros((W.shape[1], 0)))

@@ -381,3 +381,64 @@ def test_tensor_core_and_cuda_core_paths_agree_end_to_end(golden_dir):
         outs.append(W.cpu().numpy().astype(np.float64))
         assert per_atom(outs[-1], g["W_final"]) < ATOM_TOL_FP32
     assert per_atom(outs[0], outs[1]) < 2e-4
+
+
+# ---------------------------------------------------------------------------------------------- batched reconstruction (§8f.1)
+def test_batched_reconstruction_matches_reference_loop(golden_dir):
+    from onmf_ontf_ndl_b200 import reconstruct_image
+    g = load(golden_dir, "reconstruct_color")
+    rec, cnt, code = reconstruct_image(g["img"], g["W"], int(g["patch"]), int(g["stride"]), alpha=1, sub_iter=10,
+                                       stopping_diff=0.01, coder="pgd", H0=g["H0"], precision="fp64", return_code=True)
+    assert rel(code, g["codes"]) < 1e-10 and rel(rec, g["recons"]) < 1e-10 and np.array_equal(cnt, g["count"])
+    rec32, _ = reconstruct_image(g["img"], g["W"], int(g["patch"]), int(g["stride"]), alpha=1, coder="pgd", H0=g["H0"],
+                                 precision="fp32")
+    assert rel(rec32, g["recons"]) < 1e-4
+    # default H0 = the reference's RNG stream (one np.random.rand(r, 1) per patch, loop order)
+    np.random.seed(7)
+    recd, _ = reconstruct_image(g["img"], g["W"], 5, 2, precision="fp64")
+    np.random.seed(7)
+    ny, nx = len(range(0, 36 - 5, 2)), len(range(0, 40 - 5, 2))
+    H0 = np.stack([np.random.rand(25, 1)[:, 0] for _ in range(ny * nx)], 1)
+    ref, _, _ = O.reconstruct_image_loop(g["img"], g["W"], 5, 2, 1, 10, 0.01, H0)
+    assert rel(recd, ref) < 1e-10
+    # lasso_lars coder variant (image_reconstruction.py:380-383) on a gray image, stride 3
+    gray = g["img"][:, :, 0]
+    Wg = np.abs(g["W"][:25, :12]); Wg /= np.linalg.norm(Wg, axis=0)
+    recl, cntl = reconstruct_image(gray, Wg, 5, 3, alpha=0.1, coder="lasso_lars", precision="fp64")
+    refl, cntr, _ = O.reconstruct_image_loop(gray, Wg, 5, 3, 0.1, 0, 0, np.zeros((12, 200)),
+                                             coder=lambda patch, h0: c_oracle.sparse_code(patch, Wg, 0.1))
+    assert rel(recl, refl) < 1e-9 and np.array_equal(cntl, cntr) and recl.shape == gray.shape
+
+
+def test_patch_grid_mean_equals_sklearn_overlap_average():
+    from sklearn.feature_extraction.image import extract_patches_2d, reconstruct_from_patches_2d
+    rng = np.random.default_rng(0)
+    img = rng.random((17, 23))
+    P = extract_patches_2d(img, (4, 4)) + rng.random((14 * 20, 4, 4))          # ising_reconstruction.py:185,199 use these
+    ref = reconstruct_from_patches_2d(P, (17, 23))
+    R = tt(P.reshape(len(P), -1), torch.float64)
+    canvas = torch.empty(17, 23, 1, dtype=torch.float64, device=dev())
+    _lib.patch_grid_mean(R, 14, 20, 4, 1, 1, 17, 23, canvas)
+    assert rel(canvas.cpu().numpy()[:, :, 0], ref) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------------- full-length runs, fp32 bars
+@pytest.mark.parametrize("name", ["full_cfg1", "full_cfg2", "full_cfg3", "full_cfg4"])
+def test_full_length_run_fp32_bars(golden_dir, name):
+    """BASELINE.json configs at full minibatch size (cfg1 also at its full 100 iterations) in the fp32 production mode:
+    final dictionary per atom within 1e-3 of the reference's, reconstruction error within 0.5 %."""
+    g = load(golden_dir, name)
+    scale = 255.0 if name in ("full_cfg1", "full_cfg2") else 1.0
+    X = g["pool_u8"].astype(np.float64) / scale
+    ntr, k, iters, batch, alpha = int(g["n_train"]), int(g["k"]), int(g["iters"]), int(g["batch"]), float(g["alpha"])
+    np.random.seed(int(g["seed"]))
+    m = Online_NTF(X[:, :ntr, None], n_components=k, iterations=iters + 1, batch_size=batch, alpha=alpha, mode=0,
+                   learn_joint_dict=False, precision="fp32")
+    W, A, B, _ = m.train_dict_single()
+    assert float(m.history) == float(g["history"])
+    assert per_atom(W, g["W"]) < ATOM_TOL_FP32, per_atom(W, g["W"])
+    assert rel(A, g["A"]) < 2e-3 and rel(B, g["B"]) < 2e-3
+    Xe = X[:, ntr:ntr + 400]                       # the 400 held-out columns oracle/make_golden_full.py used
+    e_got = np.linalg.norm(Xe - W @ O.sparse_code_sklearn(Xe, W, alpha)) / np.linalg.norm(Xe)
+    assert abs(e_got - float(g["recon"])) <= RECON_TOL * float(g["recon"])
+    assert m.lars_stats["flagged"] <= m.lars_stats["columns"] // 1000

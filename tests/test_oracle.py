@@ -146,3 +146,12 @@ def test_gather_and_matricize_golden(golden_dir):
     Xm = O.matricize(T, int(g2["mode"]), bool(g2["joint"]))
     assert np.array_equal(Xm, g2["X"])            # (300 x N): feature f = (row*10 + col)*3 + channel
     assert Xm[(2 * 10 + 3) * 3 + 1, 5] == T[2 * 10 + 3, 1, 5]
+
+
+def test_reconstruction_loop_golden(golden_dir):
+    """oracle restatement of the per-patch reconstruction loop (image_reconstruction.py:358-406) against the fixture made
+    with the reference's own update_code_within_radius."""
+    g = load(golden_dir, "reconstruct_color")
+    rec, cnt, codes = O.reconstruct_image_loop(g["img"], g["W"], int(g["patch"]), int(g["stride"]), 1, 10, 0.01, g["H0"])
+    assert rel(codes, g["codes"]) < 1e-12 and rel(rec, g["recons"]) < 1e-12 and np.array_equal(cnt, g["count"])
+    assert cnt.max() == 9 and cnt[-1, -1] == 0          # the loop never reaches the last row/column (range(0, H-k, res))
