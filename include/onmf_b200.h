@@ -181,6 +181,12 @@ int onmf_pgd_code_columns(int dtype, const void* G, const void* Ct, int64_t n, i
 int onmf_patch_grid_mean(int dtype, const void* R, int64_t ldr, int ny, int nx, int p, int stride, int C, int H,
                          int W, void* canvas, void* count, void* stream);
 
+/* NDL motif-adjacency patches: Xt[j, q*kk + r] = has_edge(emb[j, q], emb[j, r]) for a CSR graph with
+ * sorted neighbour lists -- replaces the k*k python has_edge loop network_reconstruction_nx.py:302-305 for a batch of
+ * MCMC states (the walk itself stays on the host). */
+int onmf_motif_patches(int dtype, const int64_t* rowptr, const int32_t* colidx, int n_nodes, const int32_t* emb,
+                       int64_t n, int kk, void* Xt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

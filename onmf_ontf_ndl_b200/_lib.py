@@ -58,6 +58,7 @@ SIGNATURES = {
     "onmf_pgd_sweep": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _vp, _vp]),
     "onmf_pgd_code_columns": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _dbl, _vp, _vp]),
     "onmf_patch_grid_mean": (_i, [_i, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "onmf_motif_patches": (_i, [_i, _vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
 }
 
 _lib = None
@@ -275,3 +276,11 @@ def patch_grid_mean(R, ny, nx, p, stride, C, H, W, canvas, count=None, stream=No
     _check(load().onmf_patch_grid_mean(dt(R), _ptr(R), R.stride(0), ny, nx, p, stride, C, H, W, _ptr(canvas), _ptr(count),
                                        _stream(stream)), "onmf_patch_grid_mean")
     return canvas
+
+
+def motif_patches(rowptr, colidx, emb, out, stream=None):
+    _req(rowptr, "rowptr", torch.int64); _req(colidx, "colidx", torch.int32); _req(emb, "emb", torch.int32); _req(out, "out")
+    n, kk = emb.shape
+    _check(load().onmf_motif_patches(dt(out), _ptr(rowptr), _ptr(colidx), rowptr.shape[0] - 1, _ptr(emb), n, kk, _ptr(out),
+                                     _stream(stream)), "onmf_motif_patches")
+    return out

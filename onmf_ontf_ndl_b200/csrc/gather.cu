@@ -355,3 +355,49 @@ extern "C" int onmf_patch_grid_mean(int dtype, const void* R, int64_t ldr, int n
   ONMF_LAUNCH_CHECK("patch_grid_mean_kernel");
   return ONMF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// NDL motif-adjacency patches: X[j, q*kk + r] = G.has_edge(emb[j, q], emb[j, r])
+// (reference network_reconstruction_nx.py:302-305, one k x k patch per MCMC state).  The graph is a CSR adjacency
+// with sorted neighbour lists (both directions stored for an undirected graph); one thread per patch entry does a
+// binary search in the row of emb[j, q].  The MCMC walk that produces `emb` is sequential and stays on the host.
+// ------------------------------------------------------------------------------------------------
+namespace onmf {
+template <typename T>
+__global__ void motif_patches_kernel(const long long* __restrict__ rowptr, const int* __restrict__ colidx, int n_nodes,
+                                     const int* __restrict__ emb, long long n, int kk, T* __restrict__ Xt) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (long long)kk * kk;
+  if (idx >= n * per) return;
+  const long long j = idx / per;
+  const int e = (int)(idx - j * per);
+  const int q = e / kk, r = e - q * kk;
+  const int u = emb[j * kk + q], v = emb[j * kk + r];
+  T val = T(0);
+  if (u >= 0 && u < n_nodes && v >= 0 && v < n_nodes) {
+    long long lo = rowptr[u], hi = rowptr[u + 1];
+    while (lo < hi) {
+      long long mid = (lo + hi) >> 1;
+      int c = colidx[mid];
+      if (c < v) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < rowptr[u + 1] && colidx[lo] == v) val = T(1);
+  }
+  Xt[idx] = val;
+}
+}  // namespace onmf
+
+extern "C" int onmf_motif_patches(int dtype, const int64_t* rowptr, const int32_t* colidx, int n_nodes, const int32_t* emb,
+                                  int64_t n, int kk, void* Xt, void* stream) {
+  if (!rowptr || !colidx || !emb || !Xt || n_nodes <= 0 || n < 0 || kk <= 0) return fail(ONMF_E_ARG, "motif_patches: bad argument");
+  if (n == 0) return ONMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long tot = n * (long long)kk * kk;
+  unsigned grid = (unsigned)cdiv<long long>(tot, 256);
+  if (dtype == ONMF_F32) motif_patches_kernel<float><<<grid, 256, 0, st>>>((const long long*)rowptr, colidx, n_nodes, emb, n, kk, (float*)Xt);
+  else if (dtype == ONMF_F64) motif_patches_kernel<double><<<grid, 256, 0, st>>>((const long long*)rowptr, colidx, n_nodes, emb, n, kk, (double*)Xt);
+  else return fail(ONMF_E_ARG, "motif_patches: bad dtype");
+  ONMF_LAUNCH_CHECK("motif_patches_kernel");
+  return ONMF_OK;
+}

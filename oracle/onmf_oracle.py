@@ -372,3 +372,16 @@ def reconstruct_image_loop(A, W, k, res, alpha, sub_iter, stopping_diff, H0, cod
             pidx += 1
     rec = rec[:, :, 0] if A.ndim == 2 else rec
     return rec, cnt, (np.stack(codes, 1) if codes else np.zeros((W.shape[1], 0)))
+
+
+def motif_patches(adj_sets, emb):
+    """network_reconstruction_nx.py:302-305 for a batch of embeddings: X[q*k + r, j] = has_edge(emb[j][q], emb[j][r]);
+    adj_sets[u] = set of neighbours of u."""
+    emb = np.asarray(emb)
+    n, k = emb.shape
+    X = np.zeros((k * k, n))
+    for j in range(n):
+        for q in range(k):
+            for r in range(k):
+                X[q * k + r, j] = 1.0 if emb[j, r] in adj_sets[emb[j, q]] else 0.0
+    return X

@@ -442,3 +442,31 @@ def test_full_length_run_fp32_bars(golden_dir, name):
     e_got = np.linalg.norm(Xe - W @ O.sparse_code_sklearn(Xe, W, alpha)) / np.linalg.norm(Xe)
     assert abs(e_got - float(g["recon"])) <= RECON_TOL * float(g["recon"])
     assert m.lars_stats["flagged"] <= m.lars_stats["columns"] // 1000
+
+
+# ---------------------------------------------------------------------------------------------- on-device patch pipelines (§8f.2, §8f.4)
+def test_patch_pipeline_helpers(golden_dir):
+    from onmf_ontf_ndl_b200 import patches
+    g = load(golden_dir, "cfg1_renoir_gray")
+    np.random.seed(3)
+    X = patches.extract_random_patches(g["img"], 10, 50, precision="fp64")
+    np.random.seed(3)
+    co = np.array([[np.random.choice(g["img"].shape[0] - 10), np.random.choice(g["img"].shape[1] - 10)] for _ in range(50)])
+    assert np.array_equal(X, O.gather_patches_gray(g["img"], co, 10))            # same RNG order, exact copy
+    g2 = load(golden_dir, "cfg2_renoir_color_tensor")
+    T = patches.patches_to_tensor(patches.gather_patches(g2["img"], g2["coords"], 10, precision="fp64"), 3)
+    assert np.array_equal(T, g2["T"])                                           # the reference's (k*k, 3, N) tensor
+    # motif patches on a random graph with a self-loop and an isolated node
+    import networkx as nx
+    G = nx.gnp_random_graph(60, 0.1, seed=1)
+    G.add_edge(5, 5)
+    csr = patches.graph_to_csr(G)
+    rng = np.random.default_rng(2)
+    emb = rng.integers(0, 60, size=(300, 7))
+    Xm = patches.motif_patches(csr, emb, precision="fp32")
+    ref = O.motif_patches({u: set(G.neighbors(u)) for u in G.nodes()}, emb)
+    assert np.array_equal(Xm, ref) and Xm.shape == (49, 300) and Xm[0, np.where(emb[:, 0] == 5)[0]].all()
+    for j in range(3):                                                          # equals networkx's own has_edge
+        for q in range(7):
+            for r in range(7):
+                assert Xm[q * 7 + r, j] == float(G.has_edge(emb[j, q], emb[j, r]))
