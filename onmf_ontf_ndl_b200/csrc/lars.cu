@@ -37,6 +37,10 @@
 
 namespace onmf {
 
+#ifndef LARS_MAX_THREADS
+#define LARS_MAX_THREADS 512     // 16 warps/SM at <= 128 registers per thread (20 warps at 96 registers measured no faster)
+#endif
+
 template <typename T>
 struct LarsParams {
   const T* G;        // k x k
@@ -196,7 +200,7 @@ __global__ void pad_gram_kernel(const T* __restrict__ G, int k, int kp, T* __res
 }
 
 template <typename T, int LPC, int NA, int SMAX, bool GSM, bool MGLOB>
-__global__ void __launch_bounds__(512, 1) lars_kernel(LarsParams<T> P) {
+__global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T> P) {
   typedef typename VecOf<T>::type VT;
   constexpr int VEC = VecOf<T>::N;
   constexpr int SA = (SMAX + LPC - 1) / LPC;   // active slots per lane
@@ -775,7 +779,7 @@ static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaSt
   const size_t avail = smem_max - (gsm ? g_bytes : 0) - 256;
   int nw = (int)(avail / (GPW * grp_bytes));
   if (nw > max_warps) nw = max_warps;
-  if (nw > 16) nw = 16;
+  if (nw > LARS_MAX_THREADS / 32) nw = LARS_MAX_THREADS / 32;
   if (nw < 1) return fail(ONMF_E_UNSUPPORTED, "lasso_lars: shared memory too small for one warp");
   // spread small minibatches over all SMs instead of packing few CTAs
   long long groups = cdiv<long long>(n_upper, GPW);
@@ -845,27 +849,27 @@ static int launch_class(const T* G, const T* Ct, long long n, int k, int d, doub
   if (adaptive || first == 0) {
     LarsParams<T> Q = tier_params(0, 0, false, S1 > 0, GL && S1 == 0);
     if (adaptive) { Q.hint = &hdr->hint; Q.run_if = 0; }
-    rc = launch_tier<T, LPC, NA, S0, (GL && S1 == 0)>(Q, n, 16, st);
+    rc = launch_tier<T, LPC, NA, S0, (GL && S1 == 0)>(Q, n, 32, st);
     if (rc) return rc;
   }
   if constexpr (S1 > 0) {
     if (adaptive || first == 1) {      // tier 1 over ALL columns
       LarsParams<T> Q = tier_params(1, 4, false, S2 > 0, GL && S2 == 0);
       if (adaptive) { Q.hint = &hdr->hint; Q.run_if = 1; Q.over_thresh = &hdr->over_thresh; }
-      rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(Q, n, (GL && S2 == 0) ? 2 : 16, st);
+      rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(Q, n, (GL && S2 == 0) ? 2 : 32, st);
       if (rc) return rc;
     }
     if (adaptive || first == 0) {      // tier 1 over tier 0's overflow list
-      rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(tier_params(1, 1, true, S2 > 0, GL && S2 == 0), n, (GL && S2 == 0) ? 2 : 16, st);
+      rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(tier_params(1, 1, true, S2 > 0, GL && S2 == 0), n, (GL && S2 == 0) ? 2 : 32, st);
       if (rc) return rc;
     }
   }
   if constexpr (S2 > 0) {
-    rc = launch_tier<T, LPC, NA, S2, (GL && S3 == 0)>(tier_params(2, 2, true, S3 > 0, GL && S3 == 0), n, (GL && S3 == 0) ? 2 : 16, st);
+    rc = launch_tier<T, LPC, NA, S2, (GL && S3 == 0)>(tier_params(2, 2, true, S3 > 0, GL && S3 == 0), n, (GL && S3 == 0) ? 2 : 32, st);
     if (rc) return rc;
   }
   if constexpr (S3 > 0) {
-    rc = launch_tier<T, LPC, NA, S3, GL>(tier_params(3, 3, true, false, GL), n, GL ? 2 : 16, st);
+    rc = launch_tier<T, LPC, NA, S3, GL>(tier_params(3, 3, true, false, GL), n, GL ? 2 : 32, st);
     if (rc) return rc;
   }
   if (adaptive) {
