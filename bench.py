@@ -59,7 +59,7 @@ class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU during the timed region (NVML; same fields as the
     nvidia-smi line of B200_PROFILING.md)."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -296,7 +296,10 @@ def run_ours(args):
     fp32_peak = 148 * 128 * 2 * sm_clock / 1e12               # TFLOP/s at the observed clock
     smem_peak = 148 * 128 * sm_clock / 1e9                    # GB/s  (128 B/clk/SM)
     roofline = {"bound": "hbm", "kernel": "lars_kernel (K3 sparse coder)", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / hbm_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one tier-0 launch at cfg5, N=1 (ncu --set full,
+                # profiles/r1_lars_k256_ncu.md); only valid for that workload
+                "traffic": 4.09e8 if (args.workload == "cfg5" and world == 1) else None, "peak_source": peak_src,
                 "ms_per_launch": lars_ms, "share_of_step": lars_ms * K / elapsed_ms,
                 "note": "the coder is FP32-FMA / shared-memory bound, not HBM bound; see lars_work"}
     lars_work = {"knots_per_column": stats["knots"] / cols, "mean_active": stats["sum_active"] / max(stats["knots"], 1),

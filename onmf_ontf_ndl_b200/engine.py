@@ -120,6 +120,12 @@ class OnmfEngine:
     def _stats_ptr(self):
         return self.stats
 
+    def _lars_launches(self):
+        """kernels one onmf_lasso_lars call launches: Gram padding + the tier chain (both first-tier variants when the
+        class has more than one tier) + the scheduling-hint update (csrc/lars.cu launch_class)."""
+        k = self.k
+        return 2 if k <= 32 else 5 if k <= 64 else 6 if k <= 128 else 7
+
     # ------------------------------------------------------------------ coding only
     def sparse_code(self, Xt: torch.Tensor, W: Optional[torch.Tensor] = None, alpha=None, out=None):
         """Ht (n x k) = positive lasso_lars codes of the rows of Xt (n x d) against W (default: current)."""
@@ -144,7 +150,7 @@ class OnmfEngine:
             self.launches += 1
         _lib.lasso_lars(G, Ct, self.d, self.alpha if alpha is None else alpha, Ht, self._ws_lars,
                         max_iter=self.max_iter, stats=self._stats_ptr())
-        self.launches += 5
+        self.launches += self._lars_launches()
         return Ht
 
     # ------------------------------------------------------------------ one online step
@@ -197,13 +203,14 @@ class OnmfEngine:
                     _lib.cov(Xt, self.W, Ct, stream=main)
                 _lib.lasso_lars(self.G, Ct, self.d, self.alpha, Ht, self._ws_lars, max_iter=self.max_iter,
                                 stats=self._stats_ptr(), stream=main)
+                self.launches += 1 + self._lars_launches()
             if self.use_tc:
                 _lib.split_tf32(Ht, self.Hhi[:n], self.Hlo[:n], stream=main)
                 _lib.surrogate_partial_tc(self.Hhi[:n], self.Hlo[:n], Xhi, Xlo, self.P[cur], self._ws_sur, stream=main)
-                self.launches += 2
+                self.launches += 5            # split + 2 GEMMs + 2 fixed-order reductions
             else:
                 _lib.surrogate_partial(Ht, Xt, self.P[cur], self._ws_sur, stream=main)
-            self.launches += 8 if codes is None else 3
+                self.launches += 3            # 2 GEMMs + reduction
             if self.track_C:
                 if presplit:
                     raise _lib.OnmfKernelError("track_C needs the unsplit minibatch")

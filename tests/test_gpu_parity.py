@@ -470,3 +470,27 @@ def test_patch_pipeline_helpers(golden_dir):
         for q in range(7):
             for r in range(7):
                 assert Xm[q * 7 + r, j] == float(G.has_edge(emb[j, q], emb[j, r]))
+
+
+def test_codes_large_active_sets_all_tiers():
+    """alpha = 0 (NNLS end of the path) on d=1024, k=256: active sets far beyond 128 atoms -> every tier of the coder
+    including the global-memory one; plus the k <= 512 class."""
+    rng = np.random.default_rng(5)
+    d, k, n = 1024, 256, 6
+    W = rng.random((d, k)); W /= np.linalg.norm(W, axis=0)
+    Htrue = rng.random((k, n)) * (rng.random((k, n)) < 0.8)        # X is an exact nonnegative combination of ~200 atoms
+    X = W @ Htrue
+    Href = c_oracle.sparse_code(X, W, 0.0)
+    eng = OnmfEngine(d, k, alpha=0.0, dtype=torch.float64, device=dev(), collect_stats=True)
+    H = eng.sparse_code(tt(X.T, torch.float64), tt(W, torch.float64)).cpu().numpy().T
+    st = eng.read_stats()
+    assert st["max_active"] > 128 and st["columns"] == n, st
+    assert rel(H, Href) < 1e-6 and rel(H, Htrue) < 1e-6          # (the path ends in a long near-degenerate tail: looser bar)
+    d, k, n = 96, 300, 40                                       # k-class 4 (<= 512 atoms), more atoms than features
+    W = rng.random((d, k)); W /= np.linalg.norm(W, axis=0)
+    X = rng.random((d, n))
+    Href = c_oracle.sparse_code(X, W, 0.2)
+    H = OnmfEngine(d, k, alpha=0.2, dtype=torch.float64, device=dev()).sparse_code(tt(X.T, torch.float64), tt(W, torch.float64)).cpu().numpy().T
+    assert rel(H, Href) < CODE_TOL_FP64
+    H32 = OnmfEngine(d, k, alpha=0.2, dtype=torch.float32, device=dev()).sparse_code(tt(X.T, torch.float32), tt(W, torch.float32)).cpu().numpy().T
+    assert rel(H32, Href) < 5e-3
