@@ -29,9 +29,14 @@
 //     first (gamma = z_pos), no atom joins on the iteration after a drop, the dropped atom's covariance
 //     is recomputed exactly
 //   - "alpha increasing" bail-out, degenerate-pivot rejection (cov := 0), max_iter.
-// Columns whose active set outgrows a tier's slot count are queued (device-side list) for the next tier:
-// tier 0 = 64 slots (32 for k <= 32), tier 1 = 128 slots in shared memory, tier 2 = k slots with M in global.
+// Columns whose active set outgrows a tier's slot count are queued (device-side list) and re-walked by the next tier.
+// k <= 128: 32 -> 64 -> 128 slots, all in shared memory.  k > 128: a HYBRID first tier with 64 slots whose packed
+// inverse keeps rows 0..39 in shared memory (16 warps/SM) and rows 40..63 in an L2-resident global scratch, so the
+// common case (active set <= 40) runs entirely out of shared memory and the occasional larger set costs a few global
+// accesses instead of a re-walk; then 128 slots in shared memory, then k slots with M in global memory.
 #include <math_constants.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -56,6 +61,7 @@ struct LarsParams {
   long long* ovf_list;               // columns whose active set outgrew this tier
   unsigned int* ovf_count;
   double* Mscratch;                  // last tier: per-group M storage in global memory
+  double* Mhyb;                      // hybrid tier: rows >= SPLIT of every resident group's packed M (global/L2)
   onmf_lars_stats* stats;
   int count_stats;                   // 1 on the first tier (overflow columns are counted once)
   unsigned int* over_thresh;         // counts finished columns whose active set exceeded `thresh` (scheduling feedback)
@@ -172,9 +178,10 @@ template <> struct __align__(16) SlotW<double> { int atom; int pad; double w; };
 
 // shared-memory words (4 B) one group needs: FP64 M (packed lower triangle above 32 slots, full square up to 32;
 // absent when M lives in global), g/u (FP64), slot entries, slot->atom
-template <typename T, int LPC, int SMAX, bool MGLOB>
+template <typename T, int LPC, int SMAX, bool MGLOB, int SPLIT = 0>
 __host__ __device__ constexpr int group_words() {
-  int mwords = (SMAX > 32) ? SMAX * (SMAX + 1) : 2 * SMAX * SMAX;
+  // SPLIT > 0: only the first SPLIT rows of the packed triangle live in shared memory, the rest in global scratch
+  int mwords = (SPLIT > 0) ? SPLIT * (SPLIT + 1) : (SMAX > 32) ? SMAX * (SMAX + 1) : 2 * SMAX * SMAX;
   int sv = (SMAX + LPC - 1) / LPC * LPC;
   int w = (MGLOB ? 0 : mwords) + 4 * sv + sv * (int)(sizeof(SlotW<T>) / 4) + sv;
   w = (w + 3) & ~3;                       // keep 16-byte alignment of the next group
@@ -199,7 +206,7 @@ __global__ void pad_gram_kernel(const T* __restrict__ G, int k, int kp, T* __res
   Gp[idx] = (i < k) ? G[(size_t)a * k + i] : T(0);
 }
 
-template <typename T, int LPC, int NA, int SMAX, bool GSM, bool MGLOB>
+template <typename T, int LPC, int NA, int SMAX, bool GSM, bool MGLOB, int SPLIT>
 __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T> P) {
   typedef typename VecOf<T>::type VT;
   constexpr int VEC = VecOf<T>::N;
@@ -224,17 +231,26 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
   const int gid = warp * GPW + lane / LPC;           // group id inside the CTA
   const unsigned gmask = (LPC == 32) ? 0xffffffffu : (((1u << (LPC & 31)) - 1u) << ((lane / LPC) * LPC));
   uint32_t* gbase = reinterpret_cast<uint32_t*>(smem_raw + g_bytes) +
-                    (size_t)gid * group_words<T, LPC, SMAX, MGLOB>();
+                    (size_t)gid * group_words<T, LPC, SMAX, MGLOB, SPLIT>();
+  static_assert(SPLIT == 0 || (SPLIT < SMAX && SMAX > 32 && !MGLOB), "hybrid tiers are packed, shared+global");
   constexpr int MELEMS = PACKED ? SMAX * (SMAX + 1) / 2 : SMAX * SMAX;
+  constexpr int MSM = SPLIT > 0 ? SPLIT * (SPLIT + 1) / 2 : MELEMS;   // M doubles kept in shared memory
   double* Mg;
   double* vecs;
+  double* Mx = nullptr;                                // rows >= SPLIT of the packed triangle (hybrid tiers)
   if (MGLOB) {
     Mg = P.Mscratch + ((size_t)blockIdx.x * (blockDim.x / LPC) + gid) * (size_t)MELEMS;
     vecs = reinterpret_cast<double*>(gbase);
   } else {
     Mg = reinterpret_cast<double*>(gbase);
-    vecs = Mg + MELEMS;
+    vecs = Mg + MSM;
+    if (SPLIT > 0) Mx = P.Mhyb + ((size_t)blockIdx.x * (blockDim.x / LPC) + gid) * (size_t)(MELEMS - MSM);
   }
+  // element of M by packed (or full) index: the hybrid tier keeps the tail rows in global memory (L2-resident)
+  auto Mat = [&](int idx) -> double& {
+    if (SPLIT > 0 && idx >= MSM) return Mx[idx - MSM];
+    return Mg[idx];
+  };
   double* gs = vecs;                                   // g = G[active, j]   (also a copy of w at a drop)
   double* us = vecs + SV;                              // u = M g            (also the dropped row of M)
   SlotW<T>* sw_ = reinterpret_cast<SlotW<T>*>(vecs + 2 * SV);     // (atom, normalised weight) by slot
@@ -380,8 +396,9 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
           }
         }
         __syncwarp();
-        // u = M g
-        {
+        // u = M g   (hyb: some rows of the packed triangle are in the global tail -- only when hw > SPLIT)
+        auto u_pass = [&](auto hyb) {
+          constexpr bool H = decltype(hyb)::value;
           int rb[SA];
 #pragma unroll
           for (int m = 0; m < SA; ++m) { const int p = l + LPC * m; rb[m] = p * (p + 1) / 2; }
@@ -395,12 +412,13 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
                 const int p = l + LPC * m;
                 const int idx = PACKED ? ((p <= q) ? qb + p : rb[m] + q) : q * SMAX + p;
                 const bool on = (LPC == 32) ? (p < hw) : (do_add && q < hw && p < hw);
-                if (on) u[m] += Mg[idx] * gq;
+                if (on) u[m] += (H ? Mat(idx) : Mg[idx]) * gq;
               }
             }
             qb += q + 1;
           }
-        }
+        };
+        if (SPLIT > 0 && hwW > SPLIT) u_pass(std::true_type{}); else u_pass(std::false_type{});
         double part = 0.0, su = 0.0;
 #pragma unroll
         for (int m = 0; m < SA; ++m) { part += gj[m] * u[m]; su += u[m]; }
@@ -431,7 +449,8 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
           if (LPC * m < hwW) us[l + LPC * m] = u[m];
         __syncwarp();
         // M += u u^T / sigma  (lower triangle only when packed)
-        {
+        auto upd_pass = [&](auto hyb) {
+          constexpr bool H = decltype(hyb)::value;
           int qb = 0;
 #pragma unroll 2
           for (int q = 0; q < hwW; ++q) {
@@ -442,12 +461,15 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
                 const int p = l + LPC * m;
                 const int idx = PACKED ? qb + p : q * SMAX + p;
                 const bool on = (LPC == 32) ? (PACKED ? p <= q : p < hw) : (do_add && q < hw && (PACKED ? p <= q : p < hw));
-                if (on) Mg[idx] += uq * u[m];
+                if (on) {
+                  if (H) Mat(idx) += uq * u[m]; else Mg[idx] += uq * u[m];
+                }
               }
             }
             qb += q + 1;
           }
-        }
+        };
+        if (SPLIT > 0 && hwW > SPLIT) upd_pass(std::true_type{}); else upd_pass(std::false_type{});
         __syncwarp();
         if (do_add) {
           const int hw_new = hw > qn + 1 ? hw : qn + 1;
@@ -457,8 +479,8 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
             int p = l + LPC * m;
             if (p < hw_new) {
               const double val = (p == qn) ? inv : -u[m] * inv;
-              Mg[Midx(qn, p)] = val;
-              if (!PACKED) Mg[Midx(p, qn)] = val;
+              Mat(Midx(qn, p)) = val;
+              if (!PACKED) Mat(Midx(p, qn)) = val;
               wd[m] = (p == qn) ? tau : wd[m] - tau * u[m];
               if (p == qn) { coef[m] = T(0); prev[m] = T(0); acts[qn] = j; }
             }
@@ -595,7 +617,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
           ur[m] = 0.0;
           if (LPC * m < hwD) {
             int p = l + LPC * m;
-            ur[m] = (dodrop && p < hw) ? Mg[Midx(p0, p)] : 0.0;
+            ur[m] = (dodrop && p < hw) ? Mat(Midx(p0, p)) : 0.0;
             us[p] = ur[m];
             gs[p] = wd[m];
             sur += ur[m];
@@ -612,7 +634,8 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         const double wp0 = dodrop ? gs[p0] : 0.0;
         const double rmpp = fast_rcp(mpp);
         if (dodrop) { ghost_atom = a_d; ghost_prev = gp; }
-        {
+        auto down_pass = [&](auto hyb) {
+          constexpr bool H = decltype(hyb)::value;
           int qb = 0;
 #pragma unroll 2
           for (int q = 0; q < hwD; ++q) {
@@ -623,12 +646,15 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
                 const int p = l + LPC * m;
                 const int idx = PACKED ? qb + p : q * SMAX + p;
                 const bool on = (LPC == 32) ? (PACKED ? p <= q : p < hw) : (dodrop && q < hw && (PACKED ? p <= q : p < hw));
-                if (on) Mg[idx] -= f * ur[m];
+                if (on) {
+                  if (H) Mat(idx) -= f * ur[m]; else Mg[idx] -= f * ur[m];
+                }
               }
             }
             qb += q + 1;
           }
-        }
+        };
+        if (SPLIT > 0 && hwD > SPLIT) down_pass(std::true_type{}); else down_pass(std::false_type{});
         __syncwarp();
         if (dodrop) {
           const double fw = wp0 * rmpp;
@@ -636,8 +662,8 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
           for (int m = 0; m < SA; ++m) {
             int p = l + LPC * m;
             if (p < hw) {
-              Mg[Midx(p0, p)] = 0.0;
-              if (!PACKED) Mg[Midx(p, p0)] = 0.0;
+              Mat(Midx(p0, p)) = 0.0;
+              if (!PACKED) Mat(Midx(p, p0)) = 0.0;
               wd[m] = (p == p0) ? 0.0 : wd[m] - fw * ur[m];
             }
             if (p == p0) {
@@ -768,13 +794,13 @@ static size_t ovf_scratch_groups(int kp) {
   return g;
 }
 
-template <typename T, int LPC, int NA, int SMAX, bool MGLOB>
+template <typename T, int LPC, int NA, int SMAX, bool MGLOB, int SPLIT = 0>
 static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaStream_t st) {
   constexpr int GPW = 32 / LPC;
   const int k = P.k;
   const int smem_max = max_smem_optin();
   const size_t g_bytes = round_up<size_t>((size_t)k * gram_stride<LPC, NA>() * sizeof(T), 128);
-  const size_t grp_bytes = (size_t)group_words<T, LPC, SMAX, MGLOB>() * 4;
+  const size_t grp_bytes = (size_t)group_words<T, LPC, SMAX, MGLOB, SPLIT>() * 4;
   const bool gsm = !MGLOB && g_bytes <= 72 * 1024 && (smem_max - (long)g_bytes - 256) >= (long)(2 * GPW * grp_bytes);
   const size_t avail = smem_max - (gsm ? g_bytes : 0) - 256;
   int nw = (int)(avail / (GPW * grp_bytes));
@@ -794,11 +820,11 @@ static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaSt
   }
   size_t smem = (gsm ? g_bytes : 0) + (size_t)nw * GPW * grp_bytes;
   if (gsm) {
-    auto kern = lars_kernel<T, LPC, NA, SMAX, true, MGLOB>;
+    auto kern = lars_kernel<T, LPC, NA, SMAX, true, MGLOB, SPLIT>;
     ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, nw * 32, smem, st>>>(P);
   } else {
-    auto kern = lars_kernel<T, LPC, NA, SMAX, false, MGLOB>;
+    auto kern = lars_kernel<T, LPC, NA, SMAX, false, MGLOB, SPLIT>;
     ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, nw * 32, smem, st>>>(P);
   }
@@ -809,9 +835,16 @@ static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaSt
 // workspace layout: [LarsWs | list1 (n x 8) | list2 (n x 8) | Gp (k x KP) | M scratch (last tier, k > 128)]
 static size_t ws_list_bytes(long long n) { return round_up<size_t>((size_t)n * sizeof(long long), 256); }
 static size_t ws_gp_bytes(int k, int kp) { return round_up<size_t>((size_t)k * kp * sizeof(double), 256); }
+// hybrid first tier (k > 128): 64 slots, the first 40 rows of the packed inverse in shared memory, rows 40..63 here
+constexpr int HYB_SLOTS = 64, HYB_SPLIT = 40;
+static size_t ws_hyb_bytes(int kp) {
+  if (kp <= 128) return 0;
+  size_t per = (size_t)(HYB_SLOTS * (HYB_SLOTS + 1) / 2 - HYB_SPLIT * (HYB_SPLIT + 1) / 2) * sizeof(double);
+  return round_up<size_t>((size_t)(num_sms() > 160 ? num_sms() : 160) * (LARS_MAX_THREADS / 32) * per, 256);
+}
 
 // tiers: S0 slots, then S1, S2, S3 (0 = none); the last non-zero tier keeps M in global scratch when GL
-template <typename T, int LPC, int NA, int S0, int S1, int S2, int S3, bool GL>
+template <typename T, int LPC, int NA, int S0, int S1, int S2, int S3, bool GL, int SPLIT0 = 0>
 static int launch_class(const T* G, const T* Ct, long long n, int k, int d, double alpha, int max_iter, T* Ht,
                         unsigned char* ws, onmf_lars_stats* stats, int first_tier, cudaStream_t st) {
   constexpr int KP = LPC * NA;
@@ -820,7 +853,8 @@ static int launch_class(const T* G, const T* Ct, long long n, int k, int d, doub
   long long* lists[2] = {reinterpret_cast<long long*>(ws + sizeof(LarsWs)),
                          reinterpret_cast<long long*>(ws + sizeof(LarsWs) + lb)};
   T* gp = reinterpret_cast<T*>(ws + sizeof(LarsWs) + 2 * lb);
-  double* mscr = reinterpret_cast<double*>(ws + sizeof(LarsWs) + 2 * lb + ws_gp_bytes(k, KP));
+  double* mhyb = reinterpret_cast<double*>(ws + sizeof(LarsWs) + 2 * lb + ws_gp_bytes(k, KP));
+  double* mscr = reinterpret_cast<double*>(ws + sizeof(LarsWs) + 2 * lb + ws_gp_bytes(k, KP) + ws_hyb_bytes(KP));
   ONMF_CUDA(cudaMemsetAsync(hdr, 0, LARS_WS_RESET_BYTES, st));   // everything but the persistent hint
   pad_gram_kernel<T><<<cdiv(k * KP, 256), 256, 0, st>>>(G, k, KP, gp);
   ONMF_LAUNCH_CHECK("pad_gram_kernel");
@@ -828,7 +862,7 @@ static int launch_class(const T* G, const T* Ct, long long n, int k, int d, doub
   LarsParams<T> P;
   P.G = G; P.Gp = gp; P.Ct = Ct; P.Ht = Ht; P.n = n; P.k = k; P.d = d; P.max_iter = max_iter;
   P.amin = T(alpha) / T(d);
-  P.Mscratch = nullptr; P.stats = stats;
+  P.Mscratch = nullptr; P.Mhyb = mhyb; P.stats = stats;
   // tier t reads list (t-1)&1 and appends to list t&1.  first_tier: 0 / 1 = start every column in that tier,
   // -1 = adaptive (both first-tier variants are launched, the device-side hint decides which one does the work).
   const bool adaptive = (first_tier < 0) && S1 > 0;
@@ -849,7 +883,7 @@ static int launch_class(const T* G, const T* Ct, long long n, int k, int d, doub
   if (adaptive || first == 0) {
     LarsParams<T> Q = tier_params(0, 0, false, S1 > 0, GL && S1 == 0);
     if (adaptive) { Q.hint = &hdr->hint; Q.run_if = 0; }
-    rc = launch_tier<T, LPC, NA, S0, (GL && S1 == 0)>(Q, n, 32, st);
+    rc = launch_tier<T, LPC, NA, S0, (GL && S1 == 0), SPLIT0>(Q, n, 32, st);
     if (rc) return rc;
   }
   if constexpr (S1 > 0) {
@@ -887,8 +921,8 @@ static int lasso_lars_t(const void* G, const void* Ct, long long n, int k, int d
     case 0: return launch_class<T, 8, 4, 32, 0, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
     case 1: return launch_class<T, 16, 4, 32, 64, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
     case 2: return launch_class<T, 32, 4, 32, 64, 128, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
-    case 3: return launch_class<T, 32, 8, 40, 64, 128, 256, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
-    case 4: return launch_class<T, 32, 16, 40, 64, 128, 512, true>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+    case 3: return launch_class<T, 32, 8, HYB_SLOTS, 128, 256, 0, true, HYB_SPLIT>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+    case 4: return launch_class<T, 32, 16, HYB_SLOTS, 128, 512, 0, true, HYB_SPLIT>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
   }
   return fail(ONMF_E_UNSUPPORTED, "lasso_lars: n_components > 512 not instantiated");
 }
@@ -900,7 +934,7 @@ extern "C" size_t onmf_lasso_lars_workspace(int dtype, int k, int64_t n) {
   if (c < 0 || n < 0) return 0;
   (void)dtype;
   int kp = onmf::class_kp(c);
-  size_t bytes = sizeof(onmf::LarsWs) + 2 * onmf::ws_list_bytes(n) + onmf::ws_gp_bytes(k, kp);
+  size_t bytes = sizeof(onmf::LarsWs) + 2 * onmf::ws_list_bytes(n) + onmf::ws_gp_bytes(k, kp) + onmf::ws_hyb_bytes(kp);
   if (kp > 128) bytes += onmf::ovf_scratch_groups(kp) * ((size_t)kp * (kp + 1) / 2) * sizeof(double);
   return bytes + 256;
 }

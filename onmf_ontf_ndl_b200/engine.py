@@ -124,7 +124,7 @@ class OnmfEngine:
         """kernels one onmf_lasso_lars call launches: Gram padding + the tier chain (both first-tier variants when the
         class has more than one tier) + the scheduling-hint update (csrc/lars.cu launch_class)."""
         k = self.k
-        return 2 if k <= 32 else 5 if k <= 64 else 6 if k <= 128 else 7
+        return 2 if k <= 32 else 5 if k <= 64 else 6
 
     # ------------------------------------------------------------------ coding only
     def sparse_code(self, Xt: torch.Tensor, W: Optional[torch.Tensor] = None, alpha=None, out=None):
