@@ -288,9 +288,10 @@ def run_ours(args):
     achieved = alg_bytes / (lars_ms * 1e-3) / 1e9
     cols = max(stats["columns"] + stats["overflow"], 1)
     # executed work of the solver, counted in-kernel: per knot with active size s the kernel does one k x s
-    # correlation pass (2ks flop) and ~9 s^2 flop of inverse-update / refinement passes
-    flop = 2.0 * k * stats["sum_active"] + 9.0 * stats["sum_active2"]
-    smem_bytes = (1.0 * k * stats["sum_active"] + 5.0 * stats["sum_active2"]) * tsz
+    # correlation pass (2ks flop, 4ks bytes of Gram rows through L1/shared memory) and, on the FP64 packed inverse,
+    # u = M g (2 s^2 flop, 8 s^2 bytes) + the rank-1 update of the lower triangle (s^2 flop, 8 s^2 bytes)
+    flop = 2.0 * k * stats["sum_active"] + 3.0 * stats["sum_active2"]
+    smem_bytes = 4.0 * k * stats["sum_active"] + 16.0 * stats["sum_active2"]
     lars_total_s = lars_ms * 1e-3 * K
     sm_clock = (clocks.get("sm_mhz") or 1900.0) * 1e6
     fp32_peak = 148 * 128 * 2 * sm_clock / 1e12               # TFLOP/s at the observed clock
@@ -299,7 +300,7 @@ def run_ours(args):
                 "unit": "GB/s", "frac": achieved / hbm_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one tier-0 launch at cfg5, N=1 (ncu --set full,
                 # profiles/r1_lars_k256_ncu.md); only valid for that workload
-                "traffic": 4.09e8 if (args.workload == "cfg5" and world == 1) else None, "peak_source": peak_src,
+                "traffic": 4.95e8 if (args.workload == "cfg5" and world == 1) else None, "peak_source": peak_src,
                 "ms_per_launch": lars_ms, "share_of_step": lars_ms * K / elapsed_ms,
                 "note": "the coder is FP32-FMA / shared-memory bound, not HBM bound; see lars_work"}
     lars_work = {"knots_per_column": stats["knots"] / cols, "mean_active": stats["sum_active"] / max(stats["knots"], 1),
