@@ -171,6 +171,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     d, k, n_global, alpha = WORKLOADS[args.workload]
+    if args.batch:
+        n_global = args.batch
     lo, hi = shard_range(n_global, world, rank)
     n = hi - lo
     dt = torch.float32
@@ -346,6 +348,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-cols", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0, help="override the global minibatch size (analysis only; the line says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -38,6 +38,11 @@ extern "C" {
 #define ONMF_E_UNSUPPORTED (-3)/* shape outside what the kernels were instantiated for    */
 #define ONMF_E_WORKSPACE (-4)  /* workspace too small                                     */
 
+/* process-wide options */
+#define ONMF_OPT_LARS_RESERVED_SMS 1  /* SMs the persistent LARS coder leaves free (default 0) so that kernels launched
+                                         on other streams (the dictionary update) run concurrently with it */
+int onmf_set_option(int key, int value);
+
 /* library / build identification */
 int onmf_version(void);                      /* 100*major + minor                                   */
 const char* onmf_last_error(void);
@@ -72,6 +77,11 @@ int onmf_transpose(int dtype_in, int dtype_out, const void* src, int64_t rows, i
  *           from src/ontf.py:86) and A = W.T @ W, B = W.T @ X (src/onmf.py:242-243)
  * ------------------------------------------------------------------------------------------- */
 int onmf_gram(int dtype, const void* W, int d, int k, void* G /* k x k */, void* stream);
+/* same product with a workspace: the sum over d is split into up to 16 slices (fixed-order reduction) so the small
+ * k x k output still fills the GPU */
+size_t onmf_gram_workspace(int dtype, int d, int k);
+int onmf_gram_ws(int dtype, const void* W, int d, int k, void* G, void* workspace, size_t workspace_bytes,
+                 void* stream);
 int onmf_cov(int dtype, const void* Xt, int64_t n, int d, const void* W, int k,
              void* Ct /* n x k */, void* stream);
 

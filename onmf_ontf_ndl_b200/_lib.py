@@ -39,6 +39,9 @@ SIGNATURES = {
     "onmf_gather_rows": (_i, [_i, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "onmf_transpose": (_i, [_i, _i, _vp, _i64, _i64, _vp, _vp]),
     "onmf_gram": (_i, [_i, _vp, _i, _i, _vp, _vp]),
+    "onmf_gram_workspace": (_sz, [_i, _i, _i]),
+    "onmf_gram_ws": (_i, [_i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "onmf_set_option": (_i, [_i, _i]),
     "onmf_cov": (_i, [_i, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "onmf_lasso_lars_workspace": (_sz, [_i, _i, _i64]),
     "onmf_lasso_lars": (_i, [_i, _vp, _vp, _i64, _i, _i, _dbl, _i, _vp, _vp, _sz, _vp, _vp]),
@@ -142,10 +145,26 @@ def transpose(src, out, stream=None):
     return out
 
 
-def gram(W, G, stream=None):
+OPT_LARS_RESERVED_SMS = 1
+
+
+def set_option(key, value):
+    _check(load().onmf_set_option(int(key), int(value)), "onmf_set_option")
+
+
+def gram_workspace(dtype, d, k):
+    return int(load().onmf_gram_workspace(F64 if dtype == torch.float64 else F32, d, k))
+
+
+def gram(W, G, stream=None, workspace=None):
     _req(W, "W"); _req(G, "G", W.dtype)
     d, k = W.shape
-    _check(load().onmf_gram(dt(W), _ptr(W), d, k, _ptr(G), _stream(stream)), "onmf_gram")
+    if workspace is not None:
+        _req(workspace, "workspace", torch.uint8)
+        _check(load().onmf_gram_ws(dt(W), _ptr(W), d, k, _ptr(G), _ptr(workspace), workspace.numel(), _stream(stream)),
+               "onmf_gram_ws")
+    else:
+        _check(load().onmf_gram(dt(W), _ptr(W), d, k, _ptr(G), _stream(stream)), "onmf_gram")
     return G
 
 

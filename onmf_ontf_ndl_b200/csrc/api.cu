@@ -3,8 +3,19 @@
 
 namespace onmf {
 thread_local char g_err[512] = "";
+int g_lars_reserved_sms = 0;
 }
 
 extern "C" int onmf_version(void) { return 100; }
 extern "C" const char* onmf_last_error(void) { return onmf::g_err; }
 extern "C" int onmf_built_arch(void) { return 100; }
+
+extern "C" int onmf_set_option(int key, int value) {
+  switch (key) {
+    case ONMF_OPT_LARS_RESERVED_SMS:
+      if (value < 0 || value > 64) return onmf::fail(ONMF_E_ARG, "set_option: reserved SMs must be in [0, 64]");
+      onmf::g_lars_reserved_sms = value;
+      return ONMF_OK;
+  }
+  return onmf::fail(ONMF_E_ARG, "set_option: unknown key");
+}

@@ -50,14 +50,31 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
   const bool has_row = rl < nrows;
   const T* wrow = Ws + (size_t)rl * ks;
 
+  // software pipeline over atoms: column j+1 of A (strided, L2 resident) and B[j+1, row] are requested one full atom
+  // step before they are consumed, so their latency never sits on the k-step dependency chain
+  constexpr int PF = 4;              // per-thread slice of a column of A (k <= PF * blockDim.x, else the tail is loaded directly)
+  T pend[PF];
+  T bnext = T(0);
+  auto issue_col = [&](int col) {
+    int i = 0;
+    for (int q = tid; q < k && i < PF; q += nthr) pend[i++] = A[(size_t)q * k + col];
+  };
+  auto store_col = [&](int col, T* dst) {
+    int i = 0;
+    for (int q = tid; q < k && i < PF; q += nthr) dst[q] = pend[i++];
+    for (int q = tid + PF * nthr; q < k; q += nthr) dst[q] = A[(size_t)q * k + col];
+  };
+  if (k > 1) issue_col(1);
+  T bcur = has_row ? B[(size_t)0 * d + row0 + rl] : T(0);
+
   for (int j = 0; j < k; ++j) {
     const int par = j & 1;
     const T* a = aj + par * k;
-    // prefetch next column of A into registers (strided global read, L2 resident)
-    T nxt[4];
-    int nq = 0;
-    if (j + 1 < k)
-      for (int q = tid; q < k && nq < 4; q += nthr) nxt[nq++] = A[(size_t)q * k + (j + 1)];
+    if (j + 1 < k) {
+      store_col(j + 1, aj + (par ^ 1) * k);       // requested during the previous step; nobody reads this buffer now
+      if (has_row) bnext = B[(size_t)(j + 1) * d + row0 + rl];
+    }
+    if (j + 2 < k) issue_col(j + 2);
     T acc0 = T(0), acc1 = T(0);
     if (has_row) {
       int q = tl;
@@ -72,9 +89,10 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
     T wnew = T(0);
     if (has_row) {
       const T c = T(1) / (a[j] + T(1));
-      wnew = wrow[j] - c * (dot - B[(size_t)j * d + row0 + rl]);
+      wnew = wrow[j] - c * (dot - bcur);
       wnew = wnew > T(0) ? wnew : T(0);
     }
+    bcur = bnext;
     T sq = (has_row && tl == 0) ? wnew * wnew : T(0);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
@@ -88,12 +106,6 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
         T* peer = cluster.map_shared_rank(slots, tid);
         peer[par * BCD_MAX_CLUSTER + rank] = v;
       }
-    }
-    // store the prefetched column for the next atom (other parity buffer: nobody reads it now)
-    if (j + 1 < k) {
-      int i = 0;
-      for (int q = tid; q < k && i < 4; q += nthr) aj[(par ^ 1) * k + q] = nxt[i++];
-      for (int q = tid + 4 * nthr; q < k; q += nthr) aj[(par ^ 1) * k + q] = A[(size_t)q * k + (j + 1)];
     }
     cluster.sync();
     T tot = T(0);

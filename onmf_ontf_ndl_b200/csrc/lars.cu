@@ -812,7 +812,11 @@ static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaSt
   int nw_need = (int)cdiv<long long>(groups, num_sms());
   if (nw_need < nw) nw = nw_need < 1 ? 1 : nw_need;
   long long grid_ll = cdiv<long long>(groups, nw);
-  int grid = grid_ll > num_sms() ? num_sms() : (int)grid_ll;
+  // the kernel is persistent (one CTA per SM, full register file): optionally leave a few SMs free so that the
+  // dictionary update running on another stream can be co-scheduled instead of queueing behind it
+  int sms = num_sms() - g_lars_reserved_sms;
+  if (sms < 1) sms = 1;
+  int grid = grid_ll > sms ? sms : (int)grid_ll;
   if (MGLOB) {
     long long cap = (long long)ovf_scratch_groups(LPC * NA) / (nw * GPW);
     if (cap < 1) { nw = 1; cap = (long long)ovf_scratch_groups(LPC * NA) / GPW; }

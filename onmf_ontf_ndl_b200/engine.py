@@ -27,7 +27,8 @@ from . import _lib
 class OnmfEngine:
     def __init__(self, d: int, k: int, alpha: float = 1.0, beta: Optional[float] = None,
                  dtype: torch.dtype = torch.float32, device=None, max_iter: int = 1000,
-                 process_group=None, track_C: bool = False, collect_stats: bool = False, use_tc=None):
+                 process_group=None, track_C: bool = False, collect_stats: bool = False, use_tc=None,
+                 reserve_sms: Optional[int] = None):
         if not torch.cuda.is_available():
             raise _lib.OnmfKernelError("OnmfEngine needs a CUDA device (there is no CPU path)")
         _lib.load()
@@ -69,7 +70,9 @@ class OnmfEngine:
         self.stats = torch.zeros(len(_lib.STATS_FIELDS), dtype=torch.int64, device=dev)   # in-kernel work counters
         self._collect = bool(collect_stats)
         self.main = torch.cuda.current_stream(dev)
-        self.side = torch.cuda.Stream(dev)
+        self.side = torch.cuda.Stream(dev, priority=-1)     # dictionary update / all-reduce: short kernels, scheduled first
+        self._ws_gram = torch.empty(_lib.gram_workspace(dt_, d, k), dtype=torch.uint8, device=dev)
+        self.reserve_sms = reserve_sms
         self._ev_P = torch.cuda.Event()        # P[cur] complete on main
         self._ev_W = torch.cuda.Event()        # W (for the next coding) complete on side
         self._ev_code = torch.cuda.Event()     # main finished reading W / Xt of the current step
@@ -89,11 +92,11 @@ class OnmfEngine:
                 dst.copy_(torch.as_tensor(src).to(self.device, self.dtype))
         self._derive(self.W, self.G, getattr(self, "Whi", None), getattr(self, "Wlo", None), self.main)
 
-    def _derive(self, W, G, Whi, Wlo, stream):
+    def _derive(self, W, G, Whi, Wlo, stream, use_ws=True):
         """Everything the coder needs that depends on the dictionary only: Gram matrix and (tensor-core path)
         the TF32 hi/lo split of W.  Runs right after the dictionary update, off the minibatch's critical path."""
-        _lib.gram(W, G, stream=stream)
-        self.launches += 1
+        _lib.gram(W, G, stream=stream, workspace=self._ws_gram if use_ws else None)
+        self.launches += 2 if use_ws else 1
         if self.use_tc:
             _lib.split_tf32(W, Whi, Wlo, stream=stream)
             self.launches += 1
@@ -140,7 +143,7 @@ class OnmfEngine:
         else:
             G = self._G_scratch
             Whi, Wlo = (self._Whi_s, self._Wlo_s) if self.use_tc else (None, None)
-            self._derive(W, G, Whi, Wlo, torch.cuda.current_stream(self.device))
+            self._derive(W, G, Whi, Wlo, torch.cuda.current_stream(self.device), use_ws=False)
         if self.use_tc and n > 0:
             _lib.split_tf32(Xt, self.Xhi[:n], self.Xlo[:n])
             _lib.cov_tc(self.Xhi[:n], self.Xlo[:n], Whi, Wlo, Ct)
@@ -201,8 +204,14 @@ class OnmfEngine:
                     _lib.cov_tc(Xhi, Xlo, self.Whi, self.Wlo, Ct, stream=main)
                 else:
                     _lib.cov(Xt, self.W, Ct, stream=main)
+                # The coder is a persistent kernel that owns every SM it runs on.  When it is short (few columns per
+                # GPU) the dictionary update on the side stream would otherwise queue behind it and land on the critical
+                # path; leaving one cluster's worth of SMs free lets the two overlap (costs the coder 8/148 of its rate).
+                rsv = self.reserve_sms if self.reserve_sms is not None else (8 if n * self.k <= 131072 * 256 else 0)
+                _lib.set_option(_lib.OPT_LARS_RESERVED_SMS, rsv)
                 _lib.lasso_lars(self.G, Ct, self.d, self.alpha, Ht, self._ws_lars, max_iter=self.max_iter,
                                 stats=self._stats_ptr(), stream=main)
+                _lib.set_option(_lib.OPT_LARS_RESERVED_SMS, 0)
                 self.launches += 1 + self._lars_launches()
             if self.use_tc:
                 _lib.split_tf32(Ht, self.Hhi[:n], self.Hlo[:n], stream=main)
