@@ -84,6 +84,13 @@ int onmf_gram_ws(int dtype, const void* W, int d, int k, void* G, void* workspac
                  void* stream);
 int onmf_cov(int dtype, const void* Xt, int64_t n, int d, const void* W, int k,
              void* Ct /* n x k */, void* stream);
+/* FP64-accumulated Gram of an fp32 (dtype_in = ONMF_F32) or fp64 dictionary: G64 (k x k doubles), optional fp32 copy G32
+ * (may be NULL).  This is the Gram the coder should be given (onmf_lasso_lars_g64): the active-block inverse amplifies
+ * the independent per-entry rounding of an fp32 Gram by cond(G), while the exact Gram of the stored dictionary only
+ * sees cond(W) = sqrt(cond(G)).  Sum over d split into up to 16 slices, fixed-order reduction (deterministic). */
+size_t onmf_gram_f64_workspace(int d, int k);
+int onmf_gram_f64(int dtype_in, const void* W, int d, int k, double* G64, float* G32, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K3  batched positive LARS-lasso (the sparse coder)
@@ -122,6 +129,12 @@ int onmf_lasso_lars(int dtype, const void* G, const void* Ct, int64_t n, int k, 
 int onmf_lasso_lars_ex(int dtype, const void* G, const void* Ct, int64_t n, int k, int d, double alpha,
                        int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
                        onmf_lars_stats* stats, int first_tier, void* stream);
+
+/* same, Gram supplied in FP64 (onmf_gram_f64) while covariances / codes stay in `dtype`: the correlation passes run on
+ * a working-precision copy, the active-block inverse is built from the FP64 entries.  The production fp32 path. */
+int onmf_lasso_lars_g64(int dtype, const double* G64, const void* Ct, int64_t n, int k, int d, double alpha,
+                        int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
+                        onmf_lars_stats* stats, int first_tier, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  surrogate aggregation

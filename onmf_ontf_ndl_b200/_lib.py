@@ -42,6 +42,9 @@ SIGNATURES = {
     "onmf_gram_workspace": (_sz, [_i, _i, _i]),
     "onmf_gram_ws": (_i, [_i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "onmf_set_option": (_i, [_i, _i]),
+    "onmf_gram_f64_workspace": (_sz, [_i, _i]),
+    "onmf_gram_f64": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "onmf_lasso_lars_g64": (_i, [_i, _vp, _vp, _i64, _i, _i, _dbl, _i, _vp, _vp, _sz, _vp, _i, _vp]),
     "onmf_cov": (_i, [_i, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "onmf_lasso_lars_workspace": (_sz, [_i, _i, _i64]),
     "onmf_lasso_lars": (_i, [_i, _vp, _vp, _i64, _i, _i, _dbl, _i, _vp, _vp, _sz, _vp, _vp]),
@@ -168,6 +171,21 @@ def gram(W, G, stream=None, workspace=None):
     return G
 
 
+def gram_f64_workspace(d, k):
+    return int(load().onmf_gram_f64_workspace(d, k))
+
+
+def gram_f64(W, G64, workspace, G32=None, stream=None):
+    """G64 (k x k, float64) = W^T W accumulated in FP64 from a float32 / float64 W; optional float32 copy."""
+    _req(W, "W"); _req(G64, "G64", torch.float64); _req(workspace, "workspace", torch.uint8)
+    if G32 is not None:
+        _req(G32, "G32", torch.float32)
+    d, k = W.shape
+    _check(load().onmf_gram_f64(dt(W), _ptr(W), d, k, _ptr(G64), _ptr(G32), _ptr(workspace), workspace.numel(),
+                                _stream(stream)), "onmf_gram_f64")
+    return G64
+
+
 def cov(Xt, W, Ct, stream=None):
     _req(Xt, "Xt"); _req(W, "W", Xt.dtype); _req(Ct, "Ct", Xt.dtype)
     n, d = Xt.shape
@@ -180,8 +198,15 @@ def lasso_lars_workspace(dtype, k, n):
 
 
 def lasso_lars(G, Ct, d, alpha, Ht, workspace, max_iter=1000, stats=None, stream=None, first_tier=-1):
-    _req(G, "G"); _req(Ct, "Ct", G.dtype); _req(Ht, "Ht", G.dtype); _req(workspace, "workspace", torch.uint8)
+    """G may be in the working precision of Ct / Ht, or float64 next to float32 covariances (the production path)."""
+    _req(G, "G"); _req(Ct, "Ct"); _req(Ht, "Ht", Ct.dtype); _req(workspace, "workspace", torch.uint8)
     n, k = Ct.shape
+    if G.dtype != Ct.dtype:
+        _req(G, "G", torch.float64)
+        _check(load().onmf_lasso_lars_g64(dt(Ct), _ptr(G), _ptr(Ct), n, k, d, float(alpha), int(max_iter), _ptr(Ht),
+                                          _ptr(workspace), workspace.numel(), _ptr(stats), int(first_tier), _stream(stream)),
+               "onmf_lasso_lars_g64")
+        return Ht
     _check(load().onmf_lasso_lars_ex(dt(G), _ptr(G), _ptr(Ct), n, k, d, float(alpha), int(max_iter), _ptr(Ht),
                                      _ptr(workspace), workspace.numel(), _ptr(stats), int(first_tier), _stream(stream)),
            "onmf_lasso_lars")

@@ -181,6 +181,89 @@ static int surrogate_partial_t(const T* Ht, const T* Xt, long long n, int k, int
   return ONMF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP64-accumulated Gram matrix of an fp32 (or fp64) dictionary.  The sparse coder inverts active blocks of G; an fp32
+// G carries independent rounding errors of ~6e-8 per entry which the inverse amplifies by cond(G) (~4e5 on the early
+// online dictionaries), whereas the exact Gram of the stored (fp32) W only sees cond(W) = sqrt(cond(G)).  So the Gram
+// is accumulated and kept in FP64 (k x k doubles: 0.5 MB at k = 256), upper-triangle tiles only, mirrored on reduce.
+// ------------------------------------------------------------------------------------------------
+constexpr int G64_T = 64, G64_BK = 16;
+
+template <typename Tin>
+__global__ void __launch_bounds__(256) gram64_kernel(const Tin* __restrict__ W, int d, int k, int dchunk, int ntile,
+                                                     double* __restrict__ part) {
+  __shared__ double As[G64_BK][G64_T + 2];
+  __shared__ double Bs[G64_BK][G64_T + 2];
+  // linear tile id -> (bi <= bj)
+  int t = blockIdx.x, bi = 0;
+  while (t >= ntile - bi) { t -= ntile - bi; ++bi; }
+  const int bj = bi + t;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int r0 = blockIdx.y * dchunk;
+  int r1 = r0 + dchunk;
+  if (r1 > d) r1 = d;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int rr = r0; rr < r1; rr += G64_BK) {
+    {
+      const int kk = tid >> 4, c4 = (tid & 15) * 4;
+      const int r = rr + kk;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ci = bi * G64_T + c4 + e, cj = bj * G64_T + c4 + e;
+        As[kk][c4 + e] = (r < r1 && ci < k) ? (double)W[(size_t)r * k + ci] : 0.0;
+        Bs[kk][c4 + e] = (r < r1 && cj < k) ? (double)W[(size_t)r * k + cj] : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < G64_BK; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+  double* out = part + (size_t)blockIdx.y * k * k;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = bi * G64_T + ty * 4 + i;
+    if (gi >= k) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gj = bj * G64_T + tx * 4 + j;
+      if (gj < k) out[(size_t)gi * k + gj] = acc[i][j];
+    }
+  }
+}
+
+// G64[i][j] = sum_z part[z][min-tile-ordered (i, j)] in fixed order; optional fp32 copy
+__global__ void gram64_reduce_kernel(const double* __restrict__ part, int splits, int k, double* __restrict__ G64,
+                                     float* __restrict__ G32) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= k * k) return;
+  int i = idx / k, j = idx - i * k;
+  // only tiles with bi <= bj were computed; inside a diagonal tile both orders exist and are bitwise equal
+  const bool swap = (i / G64_T) > (j / G64_T);
+  const size_t src = swap ? (size_t)j * k + i : (size_t)i * k + j;
+  double s = 0.0;
+  for (int z = 0; z < splits; ++z) s += part[(size_t)z * k * k + src];
+  G64[idx] = s;
+  if (G32) G32[idx] = (float)s;
+}
+
+static int gram64_splits(int d) {
+  int s = d / 64;
+  return s < 1 ? 1 : s > 16 ? 16 : s;
+}
+
 }  // namespace onmf
 
 using namespace onmf;
@@ -218,6 +301,31 @@ extern "C" int onmf_gram_ws(int dtype, const void* W, int d, int k, void* G, voi
   }
   if (rc) return rc;
   ONMF_LAUNCH_CHECK("gram split reduce");
+  return ONMF_OK;
+}
+
+extern "C" size_t onmf_gram_f64_workspace(int d, int k) {
+  if (d <= 0 || k <= 0) return 0;
+  return (size_t)onmf::gram64_splits(d) * k * k * sizeof(double) + 256;
+}
+
+extern "C" int onmf_gram_f64(int dtype_in, const void* W, int d, int k, double* G64, float* G32, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  using namespace onmf;
+  if (!W || !G64 || !workspace || d <= 0 || k <= 0) return fail(ONMF_E_ARG, "gram_f64: bad argument");
+  if (workspace_bytes < onmf_gram_f64_workspace(d, k)) return fail(ONMF_E_WORKSPACE, "gram_f64: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int splits = gram64_splits(d);
+  int dchunk = round_up(cdiv(d, splits), G64_BK);
+  const int ntile = cdiv(k, G64_T);
+  dim3 grid(ntile * (ntile + 1) / 2, splits);
+  double* part = (double*)workspace;
+  if (dtype_in == ONMF_F32) gram64_kernel<float><<<grid, 256, 0, st>>>((const float*)W, d, k, dchunk, ntile, part);
+  else if (dtype_in == ONMF_F64) gram64_kernel<double><<<grid, 256, 0, st>>>((const double*)W, d, k, dchunk, ntile, part);
+  else return fail(ONMF_E_ARG, "gram_f64: bad dtype");
+  ONMF_LAUNCH_CHECK("gram64_kernel");
+  gram64_reduce_kernel<<<cdiv(k * k, 256), 256, 0, st>>>(part, splits, k, G64, G32);
+  ONMF_LAUNCH_CHECK("gram64_reduce_kernel");
   return ONMF_OK;
 }
 

@@ -48,7 +48,8 @@ namespace onmf {
 
 template <typename T>
 struct LarsParams {
-  const T* G;        // k x k
+  const T* G;        // k x k   (working precision; may be null when G64 is given)
+  const double* G64; // k x k FP64 Gram (exact Gram of the stored dictionary) feeding the active-block inverse, or null
   const T* Gp;       // k x KP zero-padded copy (workspace)
   const T* Ct;       // n x k
   T* Ht;             // n x k
@@ -199,11 +200,11 @@ __host__ __device__ constexpr int gram_stride() {
 
 // G (k x k) -> Gp (k x KP) zero-padded rows, so that every Gram row read is an aligned, unpredicated vector load
 template <typename T>
-__global__ void pad_gram_kernel(const T* __restrict__ G, int k, int kp, T* __restrict__ Gp) {
+__global__ void pad_gram_kernel(const T* __restrict__ G, const double* __restrict__ G64, int k, int kp, T* __restrict__ Gp) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= k * kp) return;
   int a = idx / kp, i = idx - a * kp;
-  Gp[idx] = (i < k) ? G[(size_t)a * k + i] : T(0);
+  Gp[idx] = (i < k) ? (G64 ? (T)G64[(size_t)a * k + i] : G[(size_t)a * k + i]) : T(0);
 }
 
 template <typename T, int LPC, int NA, int SMAX, bool GSM, bool MGLOB, int SPLIT>
@@ -262,12 +263,15 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
   if (GSM) {
     for (int idx = threadIdx.x; idx < k * GS; idx += blockDim.x) {
       int a = idx / GS, i = idx - a * GS;
-      Gs[idx] = (i < k) ? P.G[(size_t)a * k + i] : T(0);
+      Gs[idx] = (i < k) ? (P.G64 ? (T)P.G64[(size_t)a * k + i] : P.G[(size_t)a * k + i]) : T(0);
     }
     __syncthreads();
   }
   const T* Gr = GSM ? Gs : P.Gp;                       // padded rows, stride GS
   auto Gat = [&](int a, int i) -> T { return Gr[a * GS + i]; };
+  // Gram entries that enter the active-block inverse: FP64 when the caller supplies the FP64 Gram
+  const double* __restrict__ G64 = P.G64;
+  auto Gd = [&](int a, int i) -> double { return G64 ? G64[(size_t)a * k + i] : (double)Gat(a, i); };
   // M element (q, p): symmetric
   auto Midx = [&](int q, int p) -> int {
     if (PACKED) return (p <= q) ? q * (q + 1) / 2 + p : p * (p + 1) / 2 + q;
@@ -386,13 +390,13 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
           u[m] = 0.0;
           if (LPC * m < hwW) {
             int p = l + LPC * m;
-            T gv = T(0);
+            double gv = 0.0;
             if (do_add && p < hw) {
               int a = acts[p];
-              if (a >= 0) gv = Gat(a, j);
+              if (a >= 0) gv = Gd(a, j);
             }
-            gj[m] = (double)gv;
-            gs[p] = (double)gv;
+            gj[m] = gv;
+            gs[p] = gv;
           }
         }
         __syncwarp();
@@ -427,13 +431,14 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
           part += __shfl_xor_sync(0xffffffffu, part, off);
           su += __shfl_xor_sync(0xffffffffu, su, off);
         }
-        const double Gjj = do_add ? (double)Gat(j, j) : 1.0;
+        const double Gjj = do_add ? Gd(j, j) : 1.0;
         const double sig = Gjj - part;
         // sklearn: diag = max(sqrt(|c - v|), eps); degenerate if diag < 1e-7  <=>  |sig| < 1e-14
         double asig = fabs(sig);
         asig = asig > 4.930380657631324e-32 ? asig : 4.930380657631324e-32;
         bool degen = asig < 1e-14;
-        if (sizeof(T) == 4) degen = degen || !(sig > 4.0 * (double)eps32 * Gjj);   // Schur complement below the rounding noise of an fp32 Gram
+        // an fp32 Gram cannot resolve a Schur complement below its own rounding noise
+        if (sizeof(T) == 4 && G64 == nullptr) degen = degen || !(sig > 4.0 * (double)eps32 * Gjj);
         if (do_add && degen) {
           // degenerate regressor (sklearn _least_angle.py:723-742): covariance zeroed, atom stays inactive
           status |= 1;
@@ -564,8 +569,15 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
 #pragma unroll
       for (int m = 0; m < NA; ++m)
         if ((inact >> m) & 1u) {
-          T v = qdiv(C - cov[m], AA - corr[m] + tiny);
-          if (v > T(0) && v < g1) g1 = v;
+          const T den = AA - corr[m] + tiny;
+          T v = qdiv(C - cov[m], den);
+          // sklearn's min_pos takes strictly positive candidates.  C is the maximum, so the numerator is >= 0 and
+          // v > 0 <=> den > 0 unless the atom TIES with the joining one (numerator exactly 0), where sklearn steps past
+          // it.  In fp64 that is a structural (measure-zero) event and is reproduced literally; in fp32 a near-tie
+          // rounds to an exact one now and then, and stepping past the atom changes the code by O(1) -- so the fp32
+          // coder takes the zero-length step (the exact-arithmetic path: both atoms join).
+          const bool ok = (sizeof(T) == 4) ? (den > T(0)) : (v > T(0));
+          if (ok && v < g1) g1 = v;
         }
       g1 = gminpos<LPC>(g1, gmask);
       T gamma = C / AA;
@@ -849,7 +861,7 @@ static size_t ws_hyb_bytes(int kp) {
 
 // tiers: S0 slots, then S1, S2, S3 (0 = none); the last non-zero tier keeps M in global scratch when GL
 template <typename T, int LPC, int NA, int S0, int S1, int S2, int S3, bool GL, int SPLIT0 = 0>
-static int launch_class(const T* G, const T* Ct, long long n, int k, int d, double alpha, int max_iter, T* Ht,
+static int launch_class(const T* G, const double* G64, const T* Ct, long long n, int k, int d, double alpha, int max_iter, T* Ht,
                         unsigned char* ws, onmf_lars_stats* stats, int first_tier, cudaStream_t st) {
   constexpr int KP = LPC * NA;
   LarsWs* hdr = reinterpret_cast<LarsWs*>(ws);
@@ -860,11 +872,11 @@ static int launch_class(const T* G, const T* Ct, long long n, int k, int d, doub
   double* mhyb = reinterpret_cast<double*>(ws + sizeof(LarsWs) + 2 * lb + ws_gp_bytes(k, KP));
   double* mscr = reinterpret_cast<double*>(ws + sizeof(LarsWs) + 2 * lb + ws_gp_bytes(k, KP) + ws_hyb_bytes(KP));
   ONMF_CUDA(cudaMemsetAsync(hdr, 0, LARS_WS_RESET_BYTES, st));   // everything but the persistent hint
-  pad_gram_kernel<T><<<cdiv(k * KP, 256), 256, 0, st>>>(G, k, KP, gp);
+  pad_gram_kernel<T><<<cdiv(k * KP, 256), 256, 0, st>>>(G, G64, k, KP, gp);
   ONMF_LAUNCH_CHECK("pad_gram_kernel");
 
   LarsParams<T> P;
-  P.G = G; P.Gp = gp; P.Ct = Ct; P.Ht = Ht; P.n = n; P.k = k; P.d = d; P.max_iter = max_iter;
+  P.G = G; P.G64 = G64; P.Gp = gp; P.Ct = Ct; P.Ht = Ht; P.n = n; P.k = k; P.d = d; P.max_iter = max_iter;
   P.amin = T(alpha) / T(d);
   P.Mscratch = nullptr; P.Mhyb = mhyb; P.stats = stats;
   // tier t reads list (t-1)&1 and appends to list t&1.  first_tier: 0 / 1 = start every column in that tier,
@@ -918,15 +930,15 @@ static int launch_class(const T* G, const T* Ct, long long n, int k, int d, doub
 }
 
 template <typename T>
-static int lasso_lars_t(const void* G, const void* Ct, long long n, int k, int d, double alpha, int max_iter,
+static int lasso_lars_t(const void* G, const double* G64, const void* Ct, long long n, int k, int d, double alpha, int max_iter,
                         void* Ht, void* ws, onmf_lars_stats* stats, int first_tier, cudaStream_t st) {
   const T* g = (const T*)G; const T* c = (const T*)Ct; T* h = (T*)Ht; unsigned char* w = (unsigned char*)ws;
   switch (k_class(k)) {
-    case 0: return launch_class<T, 8, 4, 32, 0, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
-    case 1: return launch_class<T, 16, 4, 32, 64, 0, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
-    case 2: return launch_class<T, 32, 4, 32, 64, 128, 0, false>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
-    case 3: return launch_class<T, 32, 8, HYB_SLOTS, 128, 256, 0, true, HYB_SPLIT>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
-    case 4: return launch_class<T, 32, 16, HYB_SLOTS, 128, 512, 0, true, HYB_SPLIT>(g, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+    case 0: return launch_class<T, 8, 4, 32, 0, 0, 0, false>(g, G64, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+    case 1: return launch_class<T, 16, 4, 32, 64, 0, 0, false>(g, G64, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+    case 2: return launch_class<T, 32, 4, 32, 64, 128, 0, false>(g, G64, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+    case 3: return launch_class<T, 32, 8, HYB_SLOTS, 128, 256, 0, true, HYB_SPLIT>(g, G64, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+    case 4: return launch_class<T, 32, 16, HYB_SLOTS, 128, 512, 0, true, HYB_SPLIT>(g, G64, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
   }
   return fail(ONMF_E_UNSUPPORTED, "lasso_lars: n_components > 512 not instantiated");
 }
@@ -943,19 +955,34 @@ extern "C" size_t onmf_lasso_lars_workspace(int dtype, int k, int64_t n) {
   return bytes + 256;
 }
 
-extern "C" int onmf_lasso_lars_ex(int dtype, const void* G, const void* Ct, int64_t n, int k, int d, double alpha,
-                                  int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
-                                  onmf_lars_stats* stats, int first_tier, void* stream) {
+static int lasso_lars_entry(int dtype, const void* G, const double* G64, const void* Ct, int64_t n, int k, int d,
+                            double alpha, int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
+                            onmf_lars_stats* stats, int first_tier, void* stream) {
   using namespace onmf;
-  if (!G || !Ct || !Ht || !workspace) return fail(ONMF_E_ARG, "lasso_lars: null pointer");
+  if ((!G && !G64) || !Ct || !Ht || !workspace) return fail(ONMF_E_ARG, "lasso_lars: null pointer");
   if (n < 0 || k <= 0 || d <= 0 || max_iter < 0 || !(alpha >= 0.0)) return fail(ONMF_E_ARG, "lasso_lars: bad size/alpha");
   if (dtype != ONMF_F32 && dtype != ONMF_F64) return fail(ONMF_E_ARG, "lasso_lars: bad dtype");
   if (n == 0) return ONMF_OK;
   if (workspace_bytes < onmf_lasso_lars_workspace(dtype, k, n)) return fail(ONMF_E_WORKSPACE, "lasso_lars: workspace too small");
   if ((uintptr_t)workspace % 256) return fail(ONMF_E_ARG, "lasso_lars: workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == ONMF_F32) return lasso_lars_t<float>(G, Ct, n, k, d, alpha, max_iter, Ht, workspace, stats, first_tier, st);
-  return lasso_lars_t<double>(G, Ct, n, k, d, alpha, max_iter, Ht, workspace, stats, first_tier, st);
+  // in FP64 working precision the FP64 Gram IS the working-precision Gram
+  if (dtype == ONMF_F64) return lasso_lars_t<double>(G ? G : (const void*)G64, nullptr, Ct, n, k, d, alpha, max_iter, Ht, workspace, stats, first_tier, st);
+  return lasso_lars_t<float>(G, G64, Ct, n, k, d, alpha, max_iter, Ht, workspace, stats, first_tier, st);
+}
+
+extern "C" int onmf_lasso_lars_ex(int dtype, const void* G, const void* Ct, int64_t n, int k, int d, double alpha,
+                                  int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
+                                  onmf_lars_stats* stats, int first_tier, void* stream) {
+  if (!G) return onmf::fail(ONMF_E_ARG, "lasso_lars: null pointer");
+  return lasso_lars_entry(dtype, G, nullptr, Ct, n, k, d, alpha, max_iter, Ht, workspace, workspace_bytes, stats, first_tier, stream);
+}
+
+extern "C" int onmf_lasso_lars_g64(int dtype, const double* G64, const void* Ct, int64_t n, int k, int d, double alpha,
+                                   int max_iter, void* Ht, void* workspace, size_t workspace_bytes,
+                                   onmf_lars_stats* stats, int first_tier, void* stream) {
+  if (!G64) return onmf::fail(ONMF_E_ARG, "lasso_lars: null pointer");
+  return lasso_lars_entry(dtype, nullptr, G64, Ct, n, k, d, alpha, max_iter, Ht, workspace, workspace_bytes, stats, first_tier, stream);
 }
 
 extern "C" int onmf_lasso_lars(int dtype, const void* G, const void* Ct, int64_t n, int k, int d, double alpha,

@@ -50,9 +50,11 @@ class OnmfEngine:
         self.A = torch.zeros(k, k, dtype=dt_, device=dev)
         self.B = torch.zeros(k, d, dtype=dt_, device=dev)
         self.C = torch.zeros(d, d, dtype=dt_, device=dev) if track_C else None
-        self.G = torch.empty(k, k, dtype=dt_, device=dev)          # Gram of self.W (kept in step with it)
-        self.G_next = torch.empty(k, k, dtype=dt_, device=dev)
-        self._G_scratch = torch.empty(k, k, dtype=dt_, device=dev)  # for sparse_code() against a foreign W
+        # Gram of self.W (kept in step with it): always FP64, accumulated in FP64 from the stored dictionary -- the coder
+        # inverts active blocks of it, and an fp32 Gram's per-entry rounding is amplified by cond(G) (csrc/gemm_simt.cu)
+        self.G = torch.empty(k, k, dtype=torch.float64, device=dev)
+        self.G_next = torch.empty(k, k, dtype=torch.float64, device=dev)
+        self._G_scratch = torch.empty(k, k, dtype=torch.float64, device=dev)  # for sparse_code() against a foreign W
         self.P = [torch.zeros(k, k + d, dtype=dt_, device=dev) for _ in range(2)]
         self.P2 = torch.zeros(d, d, dtype=dt_, device=dev) if track_C else None
         self._cap = 0
@@ -71,7 +73,8 @@ class OnmfEngine:
         self._collect = bool(collect_stats)
         self.main = torch.cuda.current_stream(dev)
         self.side = torch.cuda.Stream(dev, priority=-1)     # dictionary update / all-reduce: short kernels, scheduled first
-        self._ws_gram = torch.empty(_lib.gram_workspace(dt_, d, k), dtype=torch.uint8, device=dev)
+        self._ws_gram = torch.empty(_lib.gram_f64_workspace(d, k), dtype=torch.uint8, device=dev)
+        self._ws_gram_s = torch.empty(_lib.gram_f64_workspace(d, k), dtype=torch.uint8, device=dev)  # sparse_code(foreign W)
         self.reserve_sms = reserve_sms
         self._ev_P = torch.cuda.Event()        # P[cur] complete on main
         self._ev_W = torch.cuda.Event()        # W (for the next coding) complete on side
@@ -91,12 +94,14 @@ class OnmfEngine:
             else:
                 dst.copy_(torch.as_tensor(src).to(self.device, self.dtype))
         self._derive(self.W, self.G, getattr(self, "Whi", None), getattr(self, "Wlo", None), self.main)
+        # the first dictionary update (side stream) reads W, A, B and shares the Gram workspace with the derive above
+        self._ev_code.record(self.main)
 
     def _derive(self, W, G, Whi, Wlo, stream, use_ws=True):
         """Everything the coder needs that depends on the dictionary only: Gram matrix and (tensor-core path)
         the TF32 hi/lo split of W.  Runs right after the dictionary update, off the minibatch's critical path."""
-        _lib.gram(W, G, stream=stream, workspace=self._ws_gram if use_ws else None)
-        self.launches += 2 if use_ws else 1
+        _lib.gram_f64(W, G, self._ws_gram if use_ws else self._ws_gram_s, stream=stream)
+        self.launches += 2
         if self.use_tc:
             _lib.split_tf32(W, Whi, Wlo, stream=stream)
             self.launches += 1

@@ -47,9 +47,9 @@ def _run(rank, world, port, out):
             Wr, Ar, Br, _ = ref.state()
             torch.cuda.synchronize()
             tol = 1e-11 if dt == torch.float64 else 2e-4
-            ok = (float((W - Wr).abs().max()) <= tol * float(Wr.abs().max()) and
-                  float((A - Ar).abs().max()) <= tol * float(Ar.abs().max()) and
-                  float((B - Br).abs().max()) <= tol * float(Br.abs().max()))
+            errs = [float((a - b).abs().max()) / float(b.abs().max()) for a, b in ((W, Wr), (A, Ar), (B, Br))]
+            ok = all(e <= tol for e in errs)
+            out["detail_%s" % dt] = (errs, same)
             res[str(dt)] = bool(ok and same)
         else:
             res[str(dt)] = bool(same)
@@ -62,4 +62,4 @@ def test_two_ranks_match_single_rank():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_run, args=(2, port, out), nprocs=2, join=True)
-    assert out[0] and out[1]
+    assert out[0] and out[1], dict(out)

@@ -22,6 +22,11 @@ CASES = ["cfg1_renoir_gray", "cfg1_alpha0", "cfg2_renoir_color_tensor", "cfg3_bi
 CODE_TOL_FP64 = 1e-8       # north_star bar: 1e-4
 CODE_TOL_FP32 = 2e-3       # per-minibatch fp32 codes (not a north_star bar; W / recon bars below are)
 ATOM_TOL_FP32 = 1e-3       # north_star
+
+
+def c_oracle_lars_single(G, c, alpha, d):
+    return O.lars_lasso_positive(G, c, alpha, d)
+
 RECON_TOL = 5e-3           # north_star: reconstruction error within 0.5 %
 
 
@@ -494,3 +499,39 @@ def test_codes_large_active_sets_all_tiers():
     assert rel(H, Href) < CODE_TOL_FP64
     H32 = OnmfEngine(d, k, alpha=0.2, dtype=torch.float32, device=dev()).sparse_code(tt(X.T, torch.float32), tt(W, torch.float32)).cpu().numpy().T
     assert rel(H32, Href) < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------- fp32 robustness regressions
+def test_fp32_near_tie_column_and_fp64_gram(golden_dir):
+    """A column (found in the two-rank test problem) where two atoms tie within one fp32 ulp at a knot: sklearn's
+    strictly-positive step rule then steps past the second atom if the tie rounds to an exact one, which changed the fp32
+    code by 22 %.  The fp32 coder takes the zero-length step instead and must agree with the fp64 coder (and the oracle)
+    with either Gram precision; the FP64-accumulated Gram must be the correctly rounded product."""
+    z = load(golden_dir, "fp32_tie_column")
+    d, k = 64, 32
+    G64 = tt(z["G64"], torch.float64)
+    Href = c_oracle_lars_single(z["G64"], z["c32"].astype(np.float64), 0.5, d)
+    assert set(np.nonzero(Href)[0]) == {7, 10, 20, 22, 29}
+    for G in (G64, G64.float().contiguous()):
+        for reps in (1, 5):
+            Ct = tt(np.tile(z["c32"][None, :], (reps, 1)), torch.float32)
+            Ht = torch.zeros(reps, k, device=dev())
+            ws = torch.zeros(_lib.lasso_lars_workspace(torch.float32, k, reps), dtype=torch.uint8, device=dev())
+            _lib.lasso_lars(G, Ct, d, 0.5, Ht, ws)
+            torch.cuda.synchronize()
+            for r in range(reps):
+                assert rel(Ht[r].cpu().numpy().astype(np.float64), Href) < 1e-4
+    # onmf_gram_f64: fp32 dictionary, FP64 accumulation, bitwise symmetric, odd shapes
+    rng = np.random.default_rng(11)
+    for (dd, kk) in ((64, 32), (300, 49), (441, 25), (1024, 256), (70, 130)):
+        W = rng.random((dd, kk)).astype(np.float32)
+        Wd = tt(W, torch.float32)
+        G = torch.empty(kk, kk, dtype=torch.float64, device=dev())
+        G32 = torch.empty(kk, kk, dtype=torch.float32, device=dev())
+        ws = torch.empty(_lib.gram_f64_workspace(dd, kk), dtype=torch.uint8, device=dev())
+        _lib.gram_f64(Wd, G, ws, G32=G32)
+        torch.cuda.synchronize()
+        ref = W.astype(np.float64).T @ W.astype(np.float64)
+        assert np.abs(G.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+        assert torch.equal(G, G.T.contiguous())
+        assert np.array_equal(G32.cpu().numpy(), G.cpu().numpy().astype(np.float32))
