@@ -13,7 +13,8 @@ import torch
 
 F32, F64 = 0, 1
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libonmf_b200.so")
+# ONMF_B200_LIB: alternative build of the same library (kernel experiments); never a different implementation
+LIB_PATH = os.environ.get("ONMF_B200_LIB") or os.path.join(_HERE, "libonmf_b200.so")
 
 
 class OnmfKernelError(RuntimeError):

@@ -42,6 +42,9 @@
 
 namespace onmf {
 
+#ifndef LARS_PREFETCH
+#define LARS_PREFETCH 0
+#endif
 #ifndef LARS_MAX_THREADS
 #define LARS_MAX_THREADS 512     // 16 warps/SM at <= 128 registers per thread (20 warps at 96 registers measured no faster)
 #endif
@@ -299,13 +302,13 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
 
     // ---- per-column state ----
     T cov[NA];
-    unsigned inact = 0;
+    // active atoms (and the padding beyond k) carry cov = -inf: they never win the arg-max, their step-length
+    // candidate is +inf or NaN (both fail "v < g1"), and -inf stays -inf under the covariance update -- no mask tests
 #pragma unroll
     for (int m = 0; m < NA; ++m) {
       int i = atom_of(m);
       bool ok = valid && i < k;
-      cov[m] = ok ? crow[i] : T(0);
-      if (ok) inact |= 1u << m;
+      cov[m] = ok ? crow[i] : -Num<T>::inf();
     }
     T coef[SA], prev[SA];
     double wd[SA];                       // unnormalised equiangular weights M 1, maintained incrementally
@@ -329,17 +332,26 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
 
     while (!__all_sync(0xffffffffu, done)) {
       __syncwarp();
+#if LARS_PREFETCH
+      if (!GSM && LPC == 32 && hw > 0) {       // warm L1 with the first batch of Gram rows of this knot's correlation
+        constexpr int LPR = KP * (int)sizeof(T) / 128;          // pass (one 128-byte line per lane); the rows of the
+        const int ps = lane / LPR;                                // slots filled so far are known before the join
+        if (ps < UQ) {
+          const char* a = reinterpret_cast<const char*>(Gr + sw_[ps].atom * GS) + (lane % LPR) * 128;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+        }
+      }
+#endif
       // ---- 1. largest inactive covariance ----
       T best = -Num<T>::inf();
       int bi = 0x7fffffff;
 #pragma unroll
-      for (int m = 0; m < NA; ++m)
-        if ((inact >> m) & 1u) {
-          const int i = atom_of(m);
-          if (cov[m] > best || (cov[m] == best && i < bi)) { best = cov[m]; bi = i; }
-        }
+      for (int m = 0; m < NA; ++m) {
+        const int i = atom_of(m);
+        if (cov[m] > best || (cov[m] == best && i < bi)) { best = cov[m]; bi = i; }
+      }
       gargmax<LPC>(best, bi, gmask);
-      const bool any_inact = (bi != 0x7fffffff);
+      const bool any_inact = best > -Num<T>::inf();
       const T C = any_inact ? best : T(0);
       const T a_cur = C / dT;
       bool do_add = false, skip = false;
@@ -493,7 +505,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
           sw += tau * (1.0 - su);
 #pragma unroll
           for (int m = 0; m < NA; ++m)
-            if (atom_of(m) == j) inact &= ~(1u << m);
+            if (atom_of(m) == j) cov[m] = -Num<T>::inf();
           hw = hw_new;
           if (MASKED) occ |= 1ull << qn;
           ++n_act;
@@ -538,6 +550,16 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
 #pragma unroll
       for (int m = 0; m < NA; ++m) corr[m] = T(0);
       for (int q0 = 0; q0 < hwL; q0 += UQ) {
+#if LARS_PREFETCH
+        if (!GSM && LPC == 32 && q0 + UQ < hwL) {
+          constexpr int LPR = KP * (int)sizeof(T) / 128;
+          const int ps = lane / LPR;
+          if (ps < UQ) {
+            const char* a = reinterpret_cast<const char*>(Gr + sw_[(q0 + UQ + ps) < SV ? (q0 + UQ + ps) : (SV - 1)].atom * GS) + (lane % LPR) * 128;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+          }
+        }
+#endif
         // free slots (and slots beyond this group's high-water mark) hold (atom 0, weight 0): no masking needed
         SlotW<T> e[UQ];
 #pragma unroll
@@ -567,18 +589,17 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
       // ---- 6. step length ----
       T g1 = Num<T>::big();
 #pragma unroll
-      for (int m = 0; m < NA; ++m)
-        if ((inact >> m) & 1u) {
-          const T den = AA - corr[m] + tiny;
-          T v = qdiv(C - cov[m], den);
-          // sklearn's min_pos takes strictly positive candidates.  C is the maximum, so the numerator is >= 0 and
-          // v > 0 <=> den > 0 unless the atom TIES with the joining one (numerator exactly 0), where sklearn steps past
-          // it.  In fp64 that is a structural (measure-zero) event and is reproduced literally; in fp32 a near-tie
-          // rounds to an exact one now and then, and stepping past the atom changes the code by O(1) -- so the fp32
-          // coder takes the zero-length step (the exact-arithmetic path: both atoms join).
-          const bool ok = (sizeof(T) == 4) ? (den > T(0)) : (v > T(0));
-          if (ok && v < g1) g1 = v;
-        }
+      for (int m = 0; m < NA; ++m) {
+        const T den = AA - corr[m] + tiny;
+        T v = qdiv(C - cov[m], den);
+        // sklearn's min_pos takes strictly positive candidates.  C is the maximum, so the numerator is >= 0 and
+        // v > 0 <=> den > 0 unless the atom TIES with the joining one (numerator exactly 0), where sklearn steps past
+        // it.  In fp64 that is a structural (measure-zero) event and is reproduced literally; in fp32 a near-tie
+        // rounds to an exact one now and then, and stepping past the atom changes the code by O(1) -- so the fp32
+        // coder takes the zero-length step (the exact-arithmetic path: both atoms join).
+        const bool ok = (sizeof(T) == 4) ? (den > T(0)) : (v > T(0));
+        if (ok && v < g1) g1 = v;
+      }
       g1 = gminpos<LPC>(g1, gmask);
       T gamma = C / AA;
       gamma = g1 < gamma ? g1 : gamma;
@@ -609,7 +630,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         }
 #pragma unroll
         for (int m = 0; m < NA; ++m)
-          if ((inact >> m) & 1u) cov[m] -= gamma * corr[m];
+          cov[m] -= gamma * corr[m];
         ++st_knots;
         st_s += (unsigned)n_act;
         st_s2 += (unsigned)(n_act * n_act);
@@ -714,7 +735,6 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
           for (int m = 0; m < NA; ++m)
             if (atom_of(m) == a_d) {
               cov[m] = crow[a_d] - part;
-              inact |= 1u << m;
             }
         }
       }
