@@ -180,12 +180,12 @@ template <typename T> struct SlotW;
 template <> struct __align__(8) SlotW<float> { int atom; float w; };
 template <> struct __align__(16) SlotW<double> { int atom; int pad; double w; };
 
-// shared-memory words (4 B) one group needs: FP64 M (packed lower triangle above 32 slots, full square up to 32;
-// absent when M lives in global), g/u (FP64), slot entries, slot->atom
+// shared-memory words (4 B) one group needs: the FP64 factor V (packed columns; absent when it lives in global),
+// g/t (FP64), slot entries, slot->atom
 template <typename T, int LPC, int SMAX, bool MGLOB, int SPLIT = 0>
 __host__ __device__ constexpr int group_words() {
-  // SPLIT > 0: only the first SPLIT rows of the packed triangle live in shared memory, the rest in global scratch
-  int mwords = (SPLIT > 0) ? SPLIT * (SPLIT + 1) : (SMAX > 32) ? SMAX * (SMAX + 1) : 2 * SMAX * SMAX;
+  // SPLIT > 0: only the first SPLIT columns of the packed factor live in shared memory, the rest in global scratch
+  int mwords = (SPLIT > 0) ? SPLIT * (SPLIT + 1) : SMAX * (SMAX + 1);
   int sv = (SMAX + LPC - 1) / LPC * LPC;
   int w = (MGLOB ? 0 : mwords) + 4 * sv + sv * (int)(sizeof(SlotW<T>) / 4) + sv;
   w = (w + 3) & ~3;                       // keep 16-byte alignment of the next group
@@ -219,8 +219,6 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
   constexpr int GPW = 32 / LPC;        // columns per warp
   constexpr int KP = LPC * NA;
   constexpr int GS = GSM ? gram_stride<LPC, NA>() : KP;   // row stride of the Gram copy this kernel reads
-  constexpr bool MASKED = (SMAX <= 64);   // slot occupancy kept in a 64-bit register mask
-  constexpr bool PACKED = (SMAX > 32);    // M stored as packed lower triangle
   constexpr int UQ = (NA >= 16 || sizeof(T) == 8) ? 2 : 4;  // Gram rows in flight per correlation-pass batch
   static_assert(NA % VEC == 0 && SMAX % 4 == 0, "bad tile shape");
 
@@ -236,12 +234,15 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
   const unsigned gmask = (LPC == 32) ? 0xffffffffu : (((1u << (LPC & 31)) - 1u) << ((lane / LPC) * LPC));
   uint32_t* gbase = reinterpret_cast<uint32_t*>(smem_raw + g_bytes) +
                     (size_t)gid * group_words<T, LPC, SMAX, MGLOB, SPLIT>();
-  static_assert(SPLIT == 0 || (SPLIT < SMAX && SMAX > 32 && !MGLOB), "hybrid tiers are packed, shared+global");
-  constexpr int MELEMS = PACKED ? SMAX * (SMAX + 1) / 2 : SMAX * SMAX;
-  constexpr int MSM = SPLIT > 0 ? SPLIT * (SPLIT + 1) / 2 : MELEMS;   // M doubles kept in shared memory
+  static_assert(SPLIT == 0 || (SPLIT < SMAX && !MGLOB), "hybrid tiers keep the first SPLIT columns in shared memory");
+  // V: the inverse Cholesky factor of the active Gram block, G_AA^-1 = V V^T, V upper triangular in join order.
+  // Column i (the atom in slot i) is stored packed at [i(i+1)/2, i(i+1)/2 + i]: lanes reading one column touch
+  // consecutive doubles, a lane walking down its own column touches offsets whose banks differ per half-warp.
+  constexpr int MELEMS = SMAX * (SMAX + 1) / 2;
+  constexpr int MSM = SPLIT > 0 ? SPLIT * (SPLIT + 1) / 2 : MELEMS;   // doubles of V kept in shared memory
   double* Mg;
   double* vecs;
-  double* Mx = nullptr;                                // rows >= SPLIT of the packed triangle (hybrid tiers)
+  double* Mx = nullptr;                                // columns >= SPLIT of V (hybrid tiers)
   if (MGLOB) {
     Mg = P.Mscratch + ((size_t)blockIdx.x * (blockDim.x / LPC) + gid) * (size_t)MELEMS;
     vecs = reinterpret_cast<double*>(gbase);
@@ -250,15 +251,10 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
     vecs = Mg + MSM;
     if (SPLIT > 0) Mx = P.Mhyb + ((size_t)blockIdx.x * (blockDim.x / LPC) + gid) * (size_t)(MELEMS - MSM);
   }
-  // element of M by packed (or full) index: the hybrid tier keeps the tail rows in global memory (L2-resident)
-  auto Mat = [&](int idx) -> double& {
-    if (SPLIT > 0 && idx >= MSM) return Mx[idx - MSM];
-    return Mg[idx];
-  };
-  double* gs = vecs;                                   // g = G[active, j]   (also a copy of w at a drop)
-  double* us = vecs + SV;                              // u = M g            (also the dropped row of M)
+  double* gs = vecs;                                   // g = G[active, j]
+  double* us = vecs + SV;                              // t = V^T g
   SlotW<T>* sw_ = reinterpret_cast<SlotW<T>*>(vecs + 2 * SV);     // (atom, normalised weight) by slot
-  int* acts = reinterpret_cast<int*>(sw_ + SV);        // slot -> atom (-1 = free)
+  int* acts = reinterpret_cast<int*>(sw_ + SV);        // slot -> atom (-1 beyond the active count)
 
   // atom owned by (lane l, register m): VEC consecutive atoms per lane per vector load
   auto atom_of = [&](int m) -> int { return ((m / VEC) * LPC + l) * VEC + (m % VEC); };
@@ -272,19 +268,109 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
   }
   const T* Gr = GSM ? Gs : P.Gp;                       // padded rows, stride GS
   auto Gat = [&](int a, int i) -> T { return Gr[a * GS + i]; };
-  // Gram entries that enter the active-block inverse: FP64 when the caller supplies the FP64 Gram
+  // Gram entries that enter the factor: FP64 when the caller supplies the FP64 Gram
   const double* __restrict__ G64 = P.G64;
   auto Gd = [&](int a, int i) -> double { return G64 ? G64[(size_t)a * k + i] : (double)Gat(a, i); };
-  // M element (q, p): symmetric
-  auto Midx = [&](int q, int p) -> int {
-    if (PACKED) return (p <= q) ? q * (q + 1) / 2 + p : p * (p + 1) / 2 + q;
-    return q * SMAX + p;
-  };
 
   const T tiny = T(1.1754943508222875e-38);      // np.finfo(np.float32).tiny
   const T eps32 = T(1.1920928955078125e-07);     // np.finfo(np.float32).eps  (equality_tolerance)
   const T dT = T(P.d);
   const T amin = P.amin;
+
+  int ci[SA];                                    // start of this lane's own columns in the packed factor
+#pragma unroll
+  for (int m = 0; m < SA; ++m) { const int i = l + LPC * m; ci[m] = i * (i + 1) / 2; }
+
+  // ---- the two sweeps over the packed factor ----
+  // Columns >= SPLIT of a hybrid tier live in the global tail (Mx); the sweeps are compiled twice and the
+  // shared-memory-only version runs while the active set fits the shared part.
+  // t_i = sum_{p <= i} V[p][i] src[p]   for the slots i < lim of the groups with `on`; src (shared) has nW valid entries
+  auto sweep_t = [&](double (&t)[SA], const double* src, int nW, int lim, bool on) {
+    int ie[SA];
+#pragma unroll
+    for (int m = 0; m < SA; ++m) { const int i = l + LPC * m; ie[m] = (on && i < lim) ? i : -1; }
+    const int mMax = (nW + LPC - 1) / LPC;
+    if (SPLIT > 0 && nW > SPLIT) {
+      const double* colp[SA];                    // generic pointers: a lane's column is in shared or in global memory
+#pragma unroll
+      for (int m = 0; m < SA; ++m) colp[m] = (l + LPC * m >= SPLIT) ? (Mx + (ci[m] - MSM)) : (Mg + ci[m]);
+#pragma unroll 2
+      for (int p = 0; p < nW; ++p) {
+        const double sp = src[p];
+#pragma unroll
+        for (int m = 0; m < SA; ++m)
+          if (m < mMax && p <= ie[m]) t[m] += colp[m][p] * sp;
+      }
+    } else {
+#pragma unroll 4
+      for (int p = 0; p < nW; ++p) {
+        const double sp = src[p];
+#pragma unroll
+        for (int m = 0; m < SA; ++m)
+          if (m < mMax && p <= ie[m]) t[m] += Mg[ci[m] + p] * sp;
+      }
+    }
+  };
+  // u_p = sum_{p <= i < lim} V[p][i] src[i]
+  auto sweep_u = [&](double (&u)[SA], const double* src, int nW, int lim, bool on) {
+    int pe[SA];
+#pragma unroll
+    for (int m = 0; m < SA; ++m) pe[m] = on ? (l + LPC * m) : 0x7fffffff;
+    const int lim_e = (LPC == 32) ? nW : (on ? lim : 0);
+    const int nS = (SPLIT > 0 && nW > SPLIT) ? SPLIT : nW;
+    const double* rp = Mg + l;                     // &V[l][i] for the current column i
+#pragma unroll 4
+    for (int i = 0; i < nS; ++i) {
+      const double si = src[i];
+#pragma unroll
+      for (int m = 0; m < SA; ++m)
+        if (LPC * m <= i && pe[m] <= i && (LPC == 32 || i < lim_e)) u[m] += rp[LPC * m] * si;
+      rp += i + 1;
+    }
+    if (SPLIT > 0 && nW > SPLIT) {
+      rp = Mx + l;
+#pragma unroll 2
+      for (int i = SPLIT; i < nW; ++i) {
+        const double si = src[i];
+#pragma unroll
+        for (int m = 0; m < SA; ++m)
+          if (LPC * m <= i && pe[m] <= i && (LPC == 32 || i < lim_e)) u[m] += rp[LPC * m] * si;
+        rp += i + 1;
+      }
+    }
+  };
+  auto Vld = [&](int idx) -> double { return (SPLIT > 0 && idx >= MSM) ? Mx[idx - MSM] : Mg[idx]; };
+  auto Vst = [&](int idx, double v) {
+    if (SPLIT > 0 && idx >= MSM) Mx[idx - MSM] = v; else Mg[idx] = v;
+  };
+  // column `s` of the factor for the atom `a` joining the atoms in slots 0..s-1 (groups with `on`); sW = warp-wide
+  // bound on s.  Returns the pivot sigma = G_aa - |t|^2; u = G_AA^-1 G[A, a] is left in u[], the column is NOT written.
+  auto border = [&](int a, int s, int sW, bool on, double (&u)[SA]) -> double {
+#pragma unroll
+    for (int m = 0; m < SA; ++m) {
+      if (LPC * m < sW) {
+        const int p = l + LPC * m;
+        double gv = 0.0;
+        if (on && p < s) gv = Gd(acts[p], a);
+        gs[p] = gv;
+      }
+    }
+    __syncwarp();
+    double t[SA];
+#pragma unroll
+    for (int m = 0; m < SA; ++m) { t[m] = 0.0; u[m] = 0.0; }
+    sweep_t(t, gs, sW, s, on);
+    double tt = 0.0;
+#pragma unroll
+    for (int m = 0; m < SA; ++m) {
+      tt += t[m] * t[m];
+      if (LPC * m < sW) us[l + LPC * m] = t[m];
+    }
+    tt = gsum<LPC>(tt);
+    __syncwarp();
+    sweep_u(u, us, sW, s, on);
+    return (on ? Gd(a, a) : 1.0) - tt;
+  };
 
   unsigned long long st_knots = 0, st_s = 0, st_s2 = 0, st_drops = 0, st_flag = 0, st_cols = 0, st_ovf = 0;
   int st_maxact = 0;
@@ -301,17 +387,18 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
     const T* crow = P.Ct + (size_t)col * k;
 
     // ---- per-column state ----
-    T cov[NA];
     // active atoms (and the padding beyond k) carry cov = -inf: they never win the arg-max, their step-length
     // candidate is +inf or NaN (both fail "v < g1"), and -inf stays -inf under the covariance update -- no mask tests
+    T cov[NA];
 #pragma unroll
     for (int m = 0; m < NA; ++m) {
       int i = atom_of(m);
       bool ok = valid && i < k;
       cov[m] = ok ? crow[i] : -Num<T>::inf();
     }
+    // per-slot registers; slots are compact (0..n_act-1 in join order), everything beyond n_act is zero
     T coef[SA], prev[SA];
-    double wd[SA];                       // unnormalised equiangular weights M 1, maintained incrementally
+    double wd[SA];                       // unnormalised equiangular weights G_AA^-1 1, maintained incrementally
 #pragma unroll
     for (int m = 0; m < SA; ++m) {
       coef[m] = T(0); prev[m] = T(0); wd[m] = 0.0;
@@ -320,8 +407,8 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
       acts[l + LPC * m] = -1;
     }
     double sw = 0.0;                     // sum of wd (group-uniform)
-    int n_iter = 0, n_act = 0, hw = 0, status = 0, max_act = 0;
-    unsigned long long occ = 0;          // occupied slots (MASKED variants)
+    int n_iter = 0, n_act = 0, status = 0, max_act = 0;
+    unsigned kn_s = 0, kn_s2 = 0;        // per-column work counters (flushed to the 64-bit totals once per column)
     bool drop = false, done = !valid;
     int dslot = 0;
     T a_prev = T(0);
@@ -332,16 +419,6 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
 
     while (!__all_sync(0xffffffffu, done)) {
       __syncwarp();
-#if LARS_PREFETCH
-      if (!GSM && LPC == 32 && hw > 0) {       // warm L1 with the first batch of Gram rows of this knot's correlation
-        constexpr int LPR = KP * (int)sizeof(T) / 128;          // pass (one 128-byte line per lane); the rows of the
-        const int ps = lane / LPR;                                // slots filled so far are known before the join
-        if (ps < UQ) {
-          const char* a = reinterpret_cast<const char*>(Gr + sw_[ps].atom * GS) + (lane % LPR) * 128;
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-        }
-      }
-#endif
       // ---- 1. largest inactive covariance ----
       T best = -Num<T>::inf();
       int bi = 0x7fffffff;
@@ -373,84 +450,23 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         }
       }
 
-      // ---- 2. atom j joins: border M, update w = M 1 incrementally ----
+      // ---- 2. atom j joins slot n_act: new column of the factor, w = G_AA^-1 1 updated incrementally ----
       if (__any_sync(0xffffffffu, do_add)) {
         const int j = bi;
-        int qn;
-        if (MASKED) {
-          qn = (~occ == 0ull) ? 64 : (__ffsll((long long)~occ) - 1);
-        } else {
-          int cand = 0x7fffffff;
-#pragma unroll
-          for (int m = 0; m < SA; ++m) {
-            int p = l + LPC * m;
-            if (do_add && p < hw && acts[p] < 0 && p < cand) cand = p;
-          }
-          cand = __reduce_min_sync(gmask, cand);
-          qn = (cand == 0x7fffffff) ? hw : cand;
-        }
-        if (do_add && qn >= SMAX) {       // active set outgrew this tier: hand the column to the next one
+        if (do_add && n_act >= SMAX) {       // active set outgrew this tier: hand the column to the next one
           status |= 8;
           done = true;
           do_add = false;
         }
-        const int hwW = __reduce_max_sync(0xffffffffu, do_add ? hw : 0);
-        double gj[SA], u[SA];
-#pragma unroll
-        for (int m = 0; m < SA; ++m) {
-          gj[m] = 0.0;
-          u[m] = 0.0;
-          if (LPC * m < hwW) {
-            int p = l + LPC * m;
-            double gv = 0.0;
-            if (do_add && p < hw) {
-              int a = acts[p];
-              if (a >= 0) gv = Gd(a, j);
-            }
-            gj[m] = gv;
-            gs[p] = gv;
-          }
-        }
-        __syncwarp();
-        // u = M g   (hyb: some rows of the packed triangle are in the global tail -- only when hw > SPLIT)
-        auto u_pass = [&](auto hyb) {
-          constexpr bool H = decltype(hyb)::value;
-          int rb[SA];
-#pragma unroll
-          for (int m = 0; m < SA; ++m) { const int p = l + LPC * m; rb[m] = p * (p + 1) / 2; }
-          int qb = 0;
-#pragma unroll 2
-          for (int q = 0; q < hwW; ++q) {
-            const double gq = gs[q];
-#pragma unroll
-            for (int m = 0; m < SA; ++m) {
-              if (LPC * m < hwW) {
-                const int p = l + LPC * m;
-                const int idx = PACKED ? ((p <= q) ? qb + p : rb[m] + q) : q * SMAX + p;
-                const bool on = (LPC == 32) ? (p < hw) : (do_add && q < hw && p < hw);
-                if (on) u[m] += (H ? Mat(idx) : Mg[idx]) * gq;
-              }
-            }
-            qb += q + 1;
-          }
-        };
-        if (SPLIT > 0 && hwW > SPLIT) u_pass(std::true_type{}); else u_pass(std::false_type{});
-        double part = 0.0, su = 0.0;
-#pragma unroll
-        for (int m = 0; m < SA; ++m) { part += gj[m] * u[m]; su += u[m]; }
-#pragma unroll
-        for (int off = LPC / 2; off > 0; off >>= 1) {
-          part += __shfl_xor_sync(0xffffffffu, part, off);
-          su += __shfl_xor_sync(0xffffffffu, su, off);
-        }
-        const double Gjj = do_add ? Gd(j, j) : 1.0;
-        const double sig = Gjj - part;
+        const int sW = __reduce_max_sync(0xffffffffu, do_add ? n_act : 0);
+        double u[SA];
+        const double sig = border(do_add ? j : 0, n_act, sW, do_add, u);
         // sklearn: diag = max(sqrt(|c - v|), eps); degenerate if diag < 1e-7  <=>  |sig| < 1e-14
         double asig = fabs(sig);
         asig = asig > 4.930380657631324e-32 ? asig : 4.930380657631324e-32;
         bool degen = asig < 1e-14;
         // an fp32 Gram cannot resolve a Schur complement below its own rounding noise
-        if (sizeof(T) == 4 && G64 == nullptr) degen = degen || !(sig > 4.0 * (double)eps32 * Gjj);
+        if (sizeof(T) == 4 && G64 == nullptr) degen = degen || !(sig > 4.0 * (double)eps32 * Gd(do_add ? j : 0, do_add ? j : 0));
         if (do_add && degen) {
           // degenerate regressor (sklearn _least_angle.py:723-742): covariance zeroed, atom stays inactive
           status |= 1;
@@ -460,54 +476,27 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
           do_add = false;
           skip = true;
         }
-        const double inv = fast_rcp(asig);
+        double su = 0.0;
 #pragma unroll
-        for (int m = 0; m < SA; ++m)
-          if (LPC * m < hwW) us[l + LPC * m] = u[m];
-        __syncwarp();
-        // M += u u^T / sigma  (lower triangle only when packed)
-        auto upd_pass = [&](auto hyb) {
-          constexpr bool H = decltype(hyb)::value;
-          int qb = 0;
-#pragma unroll 2
-          for (int q = 0; q < hwW; ++q) {
-            const double uq = us[q] * inv;
-#pragma unroll
-            for (int m = 0; m < SA; ++m) {
-              if (LPC * m < hwW) {
-                const int p = l + LPC * m;
-                const int idx = PACKED ? qb + p : q * SMAX + p;
-                const bool on = (LPC == 32) ? (PACKED ? p <= q : p < hw) : (do_add && q < hw && (PACKED ? p <= q : p < hw));
-                if (on) {
-                  if (H) Mat(idx) += uq * u[m]; else Mg[idx] += uq * u[m];
-                }
-              }
-            }
-            qb += q + 1;
-          }
-        };
-        if (SPLIT > 0 && hwW > SPLIT) upd_pass(std::true_type{}); else upd_pass(std::false_type{});
-        __syncwarp();
+        for (int m = 0; m < SA; ++m) su += u[m];
+        su = gsum<LPC>(su);
         if (do_add) {
-          const int hw_new = hw > qn + 1 ? hw : qn + 1;
-          const double tau = (1.0 - su) * inv;           // new entry of M 1
+          const double rs = fast_rsqrt(asig);
+          const double tau = (1.0 - su) * rs * rs;         // new entry of G_AA^-1 1
+          const int cs = n_act * (n_act + 1) / 2;
 #pragma unroll
           for (int m = 0; m < SA; ++m) {
-            int p = l + LPC * m;
-            if (p < hw_new) {
-              const double val = (p == qn) ? inv : -u[m] * inv;
-              Mat(Midx(qn, p)) = val;
-              if (!PACKED) Mat(Midx(p, qn)) = val;
-              wd[m] = (p == qn) ? tau : wd[m] - tau * u[m];
-              if (p == qn) { coef[m] = T(0); prev[m] = T(0); acts[qn] = j; }
+            const int p = l + LPC * m;
+            if (p <= n_act) {
+              Vst(cs + p, (p == n_act) ? rs : -u[m] * rs);
+              wd[m] = (p == n_act) ? tau : wd[m] - tau * u[m];
+              if (p == n_act) acts[p] = j;
             }
           }
           sw += tau * (1.0 - su);
 #pragma unroll
           for (int m = 0; m < NA; ++m)
             if (atom_of(m) == j) cov[m] = -Num<T>::inf();
-          hw = hw_new;
-          if (MASKED) occ |= 1ull << qn;
           ++n_act;
           max_act = n_act > max_act ? n_act : max_act;
         }
@@ -521,13 +510,13 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
       }
       bool live = !done && !skip;
 
-      // ---- 4. normalise the equiangular weights: w = AA * M 1, AA = 1/sqrt(1^T M 1) ----
+      // ---- 4. normalise the equiangular weights: w = AA * G_AA^-1 1, AA = 1/sqrt(1^T G_AA^-1 1) ----
       if (live && !(sw > 0.0 && sw < 1e300)) {   // active Gram block numerically singular
         status |= 16;
         done = true;
         live = false;
       }
-      const int hwL = __reduce_max_sync(0xffffffffu, live ? hw : 0);
+      const int hwL = __reduce_max_sync(0xffffffffu, live ? n_act : 0);
       const double AAd = live ? fast_rsqrt(sw) : 1.0;
       const T AA = (T)AAd;
       T w[SA];
@@ -536,9 +525,8 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         w[m] = (T)(wd[m] * AAd);
         if (LPC * m < hwL) {
           const int p = l + LPC * m;
-          if (live && p < hw) {
-            const int a = acts[p];
-            SlotW<T> e; e.atom = a >= 0 ? a : 0; e.w = a >= 0 ? w[m] : T(0);
+          if (live && p < n_act) {
+            SlotW<T> e; e.atom = acts[p]; e.w = w[m];
             sw_[p] = e;
           }
         }
@@ -550,17 +538,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
 #pragma unroll
       for (int m = 0; m < NA; ++m) corr[m] = T(0);
       for (int q0 = 0; q0 < hwL; q0 += UQ) {
-#if LARS_PREFETCH
-        if (!GSM && LPC == 32 && q0 + UQ < hwL) {
-          constexpr int LPR = KP * (int)sizeof(T) / 128;
-          const int ps = lane / LPR;
-          if (ps < UQ) {
-            const char* a = reinterpret_cast<const char*>(Gr + sw_[(q0 + UQ + ps) < SV ? (q0 + UQ + ps) : (SV - 1)].atom * GS) + (lane % LPR) * 128;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-          }
-        }
-#endif
-        // free slots (and slots beyond this group's high-water mark) hold (atom 0, weight 0): no masking needed
+        // slots beyond this group's active count hold (atom 0, weight 0): no masking needed
         SlotW<T> e[UQ];
 #pragma unroll
         for (int t = 0; t < UQ; ++t) e[t] = sw_[q0 + t];
@@ -601,7 +579,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         if (ok && v < g1) g1 = v;
       }
       g1 = gminpos<LPC>(g1, gmask);
-      T gamma = C / AA;
+      T gamma = qdiv(C, AA);
       gamma = g1 < gamma ? g1 : gamma;
       T zbest = Num<T>::big();
       int zs = -1;
@@ -609,7 +587,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
       for (int m = 0; m < SA; ++m) {
         if (LPC * m < hwL) {
           int p = l + LPC * m;
-          if (live && p < hw && acts[p] >= 0) {
+          if (live && p < n_act) {
             T z = qdiv(-coef[m], w[m] + tiny);
             if (z > T(0) && z < zbest) { zbest = z; zs = p; }
           }
@@ -629,114 +607,167 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
           coef[m] = prev[m] + gamma * w[m];
         }
 #pragma unroll
-        for (int m = 0; m < NA; ++m)
-          cov[m] -= gamma * corr[m];
-        ++st_knots;
-        st_s += (unsigned)n_act;
-        st_s2 += (unsigned)(n_act * n_act);
+        for (int m = 0; m < NA; ++m) cov[m] -= gamma * corr[m];
+        kn_s += (unsigned)n_act;
+        kn_s2 += (unsigned)(n_act * n_act);
       }
 
-      // ---- 8. atom leaves: Schur downdate of M and of w, exact covariance of the dropped atom ----
+      // ---- 8. atom leaves slot p0: Givens downdate of the factor, Schur downdate of w, slots close up ----
+      // With r = row p0 of V:  G'^-1 = V~ (I - r r^T / r^T r) V~^T  (V~ = V without row p0).  Rotating adjacent columns
+      // p0, p0+1, ... so that r's weight moves into the running column leaves an upper-triangular factor of G'^-1 in
+      // the first n_act-1 columns; the running column (parallel to V~ r) is discarded.  O(s (s - p0)) lane-parallel work.
       const bool dodrop = live && drop;
       if (__any_sync(0xffffffffu, dodrop)) {
-        const int p0 = dodrop ? dslot : 0;
-        const int a_d = dodrop ? acts[p0] : 0;
-        const int hwD = __reduce_max_sync(0xffffffffu, dodrop ? hw : 0);
-        double ur[SA];
-        double sur = 0.0;
+        const int p0 = dodrop ? dslot : 0x7fffffff;
+        const int a_d = dodrop ? acts[dslot] : 0;
+        const int sD = __reduce_max_sync(0xffffffffu, dodrop ? n_act : 0);      // warp bound on the active count
+        // r, and m = V r = column p0 of G_AA^-1
+        double rr[SA], mv[SA], pre[SA];
         T gp = T(0);
+        double wp0 = 0.0, rp0 = 0.0, mpp = 0.0;
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
-          ur[m] = 0.0;
-          if (LPC * m < hwD) {
-            int p = l + LPC * m;
-            ur[m] = (dodrop && p < hw) ? Mat(Midx(p0, p)) : 0.0;
-            us[p] = ur[m];
-            gs[p] = wd[m];
-            sur += ur[m];
-            if (dodrop && p == p0) gp = prev[m];
+          const int i = l + LPC * m;
+          rr[m] = (dodrop && i >= p0 && i < n_act) ? Vld(ci[m] + p0) : 0.0;
+          mv[m] = 0.0;
+          if (LPC * m < sD) us[i] = rr[m];
+          if (i == p0) { gp = prev[m]; wp0 = wd[m]; rp0 = rr[m]; }
+          mpp += rr[m] * rr[m];
+        }
+        gp = gsum<LPC>(gp);
+        wp0 = gsum<LPC>(wp0);
+        rp0 = gsum<LPC>(rp0);
+        mpp = gsum<LPC>(mpp);
+        if (dodrop) { ghost_atom = a_d; ghost_prev = gp; }
+        __syncwarp();
+        sweep_u(mv, us, sD, dodrop ? n_act : 0, dodrop);
+        double sum_m = 0.0;
+#pragma unroll
+        for (int m = 0; m < SA; ++m) sum_m += mv[m];
+        sum_m = gsum<LPC>(sum_m);
+        const double fw = dodrop ? wp0 * fast_rcp(mpp) : 0.0;
+        // inclusive prefix sums of r^2 over the slots (slot = l + LPC m: lanes first, then registers)
+        {
+          double run = 0.0;
+#pragma unroll
+          for (int m = 0; m < SA; ++m) {
+            double x = rr[m] * rr[m];
+#pragma unroll
+            for (int off = 1; off < LPC; off <<= 1) {
+              const double y = __shfl_up_sync(0xffffffffu, x, off, LPC);
+              if (l >= off) x += y;
+            }
+            pre[m] = x + run;
+            run += __shfl_sync(0xffffffffu, x, LPC - 1, LPC);
           }
         }
+        __syncwarp();                    // sweep_u has finished reading us[]
+        // rotation i (columns i, i+1 -> new column i) is parameterised by slot i+1: c = r_{i+1}/rho_{i+1},
+        // sn = -a_i/rho_{i+1}, a_i = r_p0 for i = p0 and rho_i afterwards, rho_i^2 = sum_{q=p0..i} r_q^2
 #pragma unroll
-        for (int off = LPC / 2; off > 0; off >>= 1) {
-          sur += __shfl_xor_sync(0xffffffffu, sur, off);
-          gp += __shfl_xor_sync(0xffffffffu, gp, off);
+        for (int m = 0; m < SA; ++m) {
+          const int i1 = l + LPC * m;                    // = i + 1
+          if (LPC * m < sD) {
+            double c = 1.0, sn = 0.0;
+            if (dodrop && i1 > p0 && i1 < n_act) {
+              const double rinv = fast_rsqrt(pre[m]);
+              const double prev2 = pre[m] - rr[m] * rr[m];
+              const double a = (i1 - 1 == p0) ? rp0 : prev2 * fast_rsqrt(prev2);
+              c = rr[m] * rinv;
+              sn = -a * rinv;
+            }
+            gs[i1] = c;
+            us[i1] = sn;
+          }
         }
         __syncwarp();
-        const double mpp = dodrop ? us[p0] : 1.0;
-        const double wp0 = dodrop ? gs[p0] : 0.0;
-        const double rmpp = fast_rcp(mpp);
-        if (dodrop) { ghost_atom = a_d; ghost_prev = gp; }
-        auto down_pass = [&](auto hyb) {
-          constexpr bool H = decltype(hyb)::value;
-          int qb = 0;
-#pragma unroll 2
-          for (int q = 0; q < hwD; ++q) {
-            const double f = us[q] * rmpp;
+        {
+          // running column R (lane = row): starts as old column p0
+          double R[SA];
+          int nrow[SA];                                   // row index after row p0 is removed (-1: this is row p0)
+#pragma unroll
+          for (int m = 0; m < SA; ++m) {
+            const int p = l + LPC * m;
+            R[m] = (dodrop && p <= p0) ? Vld(p0 * (p0 + 1) / 2 + p) : 0.0;
+            nrow[m] = (p < p0) ? p : (p == p0 ? -1 : p - 1);
+          }
+          const int iB = __reduce_min_sync(0xffffffffu, p0);
+          __syncwarp();
+          for (int i = iB; i + 1 < sD; ++i) {
+            const bool on = dodrop && i >= p0 && i + 1 < n_act;
+            const double c = gs[i + 1], sn = us[i + 1];
+            const int cn = (i + 1) * (i + 2) / 2, co = i * (i + 1) / 2;
 #pragma unroll
             for (int m = 0; m < SA; ++m) {
-              if (LPC * m < hwD) {
+              if (LPC * m <= i + 1) {
                 const int p = l + LPC * m;
-                const int idx = PACKED ? qb + p : q * SMAX + p;
-                const bool on = (LPC == 32) ? (PACKED ? p <= q : p < hw) : (dodrop && q < hw && (PACKED ? p <= q : p < hw));
-                if (on) {
-                  if (H) Mat(idx) -= f * ur[m]; else Mg[idx] -= f * ur[m];
+                if (on && p <= i + 1) {
+                  const double X = Vld(cn + p);
+                  const double nc = c * R[m] + sn * X;
+                  R[m] = c * X - sn * R[m];
+                  if (nrow[m] >= 0) Vst(co + nrow[m], nc);
                 }
               }
             }
-            qb += q + 1;
+            __syncwarp();       // the next rotation overwrites the column this one has just read
           }
-        };
-        if (SPLIT > 0 && hwD > SPLIT) down_pass(std::true_type{}); else down_pass(std::false_type{});
-        __syncwarp();
-        if (dodrop) {
-          const double fw = wp0 * rmpp;
+        }
+        // w and its sum (Schur), then close the gap: slot p+1 -> slot p for p >= p0
+        int nxt_act[SA];
 #pragma unroll
-          for (int m = 0; m < SA; ++m) {
-            int p = l + LPC * m;
-            if (p < hw) {
-              Mat(Midx(p0, p)) = 0.0;
-              if (!PACKED) Mat(Midx(p, p0)) = 0.0;
-              wd[m] = (p == p0) ? 0.0 : wd[m] - fw * ur[m];
-            }
-            if (p == p0) {
-              coef[m] = T(0); prev[m] = T(0); acts[p0] = -1;
-              SlotW<T> z; z.atom = 0; z.w = T(0);
-              sw_[p0] = z;
-            }
+        for (int m = 0; m < SA; ++m) {
+          const int p = l + LPC * m;
+          nxt_act[m] = (p + 1 < SV) ? acts[p + 1] : -1;
+          if (dodrop) wd[m] = (p < n_act && p != p0) ? wd[m] - fw * mv[m] : 0.0;
+          const T c_dn = __shfl_down_sync(0xffffffffu, coef[m], 1, LPC);
+          const T p_dn = __shfl_down_sync(0xffffffffu, prev[m], 1, LPC);
+          const double w_dn = __shfl_down_sync(0xffffffffu, wd[m], 1, LPC);
+          const T c_wr = __shfl_sync(0xffffffffu, (m + 1 < SA) ? coef[m + 1 < SA ? m + 1 : m] : T(0), 0, LPC);
+          const T p_wr = __shfl_sync(0xffffffffu, (m + 1 < SA) ? prev[m + 1 < SA ? m + 1 : m] : T(0), 0, LPC);
+          // wd[m + 1] has not been downdated yet: apply the same formula to the wrapped value
+          double w_nx = 0.0;
+          if (m + 1 < SA) {
+            const int pn = LPC * (m + 1);                 // slot of lane 0, register m + 1
+            const double wv = wd[m + 1 < SA ? m + 1 : m], mvv = mv[m + 1 < SA ? m + 1 : m];
+            w_nx = (dodrop && pn < n_act && pn != p0) ? wv - fw * mvv : (dodrop ? 0.0 : wv);
           }
-          sw = sw - wp0 - fw * (sur - mpp);
-          --n_act;
-          ++st_drops;
-          if (MASKED) occ &= ~(1ull << p0);
+          const double w_wr = __shfl_sync(0xffffffffu, w_nx, 0, LPC);
+          if (p >= p0) {
+            coef[m] = (l == LPC - 1) ? c_wr : c_dn;
+            prev[m] = (l == LPC - 1) ? p_wr : p_dn;
+            wd[m] = (l == LPC - 1) ? w_wr : w_dn;
+          }
         }
         __syncwarp();
-        int top = 0;
+#pragma unroll
+        for (int m = 0; m < SA; ++m) {
+          const int p = l + LPC * m;
+          if (p >= p0) acts[p] = nxt_act[m];
+        }
+        if (dodrop) {
+          sw = sw - wp0 - fw * (sum_m - mpp);
+          --n_act;
+          ++st_drops;
+          if (l == 0) { SlotW<T> z; z.atom = 0; z.w = T(0); sw_[n_act] = z; }
+        }
+        __syncwarp();
+        const int i1 = __reduce_max_sync(0xffffffffu, dodrop ? n_act : 0);
+        // exact covariance of the dropped atom (sklearn _least_angle.py:891)
         T part = T(0);
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
-          if (LPC * m < hwD) {
-            int p = l + LPC * m;
-            if (dodrop && p < hw) {
-              int a = acts[p];
-              if (a >= 0) {
-                top = p + 1;
-                part += Gat(a_d, a) * coef[m];
-              }
-            }
+          if (LPC * m < i1) {
+            const int p = l + LPC * m;
+            if (dodrop && p < n_act) part += Gat(a_d, acts[p]) * coef[m];
           }
         }
-        if (MASKED) top = (occ == 0ull) ? 0 : (64 - __clzll((long long)occ));
-        else top = __reduce_max_sync(gmask, top);
         part = gsum<LPC>(part);
         if (dodrop) {
-          hw = top;
 #pragma unroll
           for (int m = 0; m < NA; ++m)
-            if (atom_of(m) == a_d) {
-              cov[m] = crow[a_d] - part;
-            }
+            if (atom_of(m) == a_d) cov[m] = crow[a_d] - part;
         }
+        __syncwarp();
       }
     }  // path loop
 
@@ -756,10 +787,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
 #pragma unroll
       for (int m = 0; m < SA; ++m) {
         int p = l + LPC * m;
-        if (p < hw) {
-          int a = acts[p];
-          if (a >= 0) hrow[a] = coef[m];
-        }
+        if (p < n_act) hrow[acts[p]] = coef[m];
       }
       if (l == 0 && ghost_atom >= 0 && ghost_val != T(0)) hrow[ghost_atom] = ghost_val;
     }
@@ -777,6 +805,9 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
       }
       st_maxact = max_act > st_maxact ? max_act : st_maxact;
     }
+    st_knots += (unsigned)n_iter;
+    st_s += kn_s;
+    st_s2 += kn_s2;
     __syncwarp();
   }  // ticket loop
 
