@@ -168,7 +168,11 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   y = y * (1.5 - 0.5 * x * y * y);
   return y;
 }
-__device__ __forceinline__ float qdiv(float a, float b) { return __fdividef(a, b); }   // step-length candidates
+__device__ __forceinline__ float qdiv(float a, float b) {      // step-length candidates: a * rcp.approx(b), 2 instructions
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+  return a * r;
+}
 __device__ __forceinline__ double qdiv(double a, double b) { return a / b; }
 
 template <typename T> struct VecOf;
@@ -273,9 +277,10 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
   auto Gd = [&](int a, int i) -> double { return G64 ? G64[(size_t)a * k + i] : (double)Gat(a, i); };
 
   const T tiny = T(1.1754943508222875e-38);      // np.finfo(np.float32).tiny
-  const T eps32 = T(1.1920928955078125e-07);     // np.finfo(np.float32).eps  (equality_tolerance)
   const T dT = T(P.d);
-  const T amin = P.amin;
+  // np.finfo(np.float32).eps (sklearn's equality_tolerance); fp32 coder: alpha and the tolerance in covariance units
+  const T eps32 = (sizeof(T) == 4) ? T(1.1920928955078125e-07) * dT : T(1.1920928955078125e-07);
+  const T amin = (sizeof(T) == 4) ? P.amin * dT : P.amin;
 
   int ci[SA];                                    // start of this lane's own columns in the packed factor
 #pragma unroll
@@ -301,6 +306,12 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         for (int m = 0; m < SA; ++m)
           if (m < mMax && p <= ie[m]) t[m] += colp[m][p] * sp;
       }
+    } else if (mMax <= 1) {                          // the common case: at most LPC active atoms, one slot register
+#pragma unroll 4
+      for (int p = 0; p < nW; ++p) {
+        const double sp = src[p];
+        if (p <= ie[0]) t[0] += Mg[ci[0] + p] * sp;
+      }
     } else {
 #pragma unroll 4
       for (int p = 0; p < nW; ++p) {
@@ -319,8 +330,15 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
     const int lim_e = (LPC == 32) ? nW : (on ? lim : 0);
     const int nS = (SPLIT > 0 && nW > SPLIT) ? SPLIT : nW;
     const double* rp = Mg + l;                     // &V[l][i] for the current column i
+    const int nS1 = nS < LPC ? nS : LPC;           // columns < LPC only reach the first slot register
 #pragma unroll 4
-    for (int i = 0; i < nS; ++i) {
+    for (int i = 0; i < nS1; ++i) {
+      const double si = src[i];
+      if (pe[0] <= i && (LPC == 32 || i < lim_e)) u[0] += rp[0] * si;
+      rp += i + 1;
+    }
+#pragma unroll 2
+    for (int i = nS1; i < nS; ++i) {
       const double si = src[i];
 #pragma unroll
       for (int m = 0; m < SA; ++m)
@@ -430,7 +448,9 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
       gargmax<LPC>(best, bi, gmask);
       const bool any_inact = best > -Num<T>::inf();
       const T C = any_inact ? best : T(0);
-      const T a_cur = C / dT;
+      // recorded alpha of the knot = C / d (sklearn divides by n_samples).  The fp32 coder keeps it in covariance units
+      // (a = C, thresholds scaled by d): same decisions up to rounding, one division less per knot
+      const T a_cur = (sizeof(T) == 4) ? C : C / dT;
       bool do_add = false, skip = false;
       if (!done) {
         if (a_cur <= amin + eps32) {
@@ -466,13 +486,17 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         asig = asig > 4.930380657631324e-32 ? asig : 4.930380657631324e-32;
         bool degen = asig < 1e-14;
         // an fp32 Gram cannot resolve a Schur complement below its own rounding noise
-        if (sizeof(T) == 4 && G64 == nullptr) degen = degen || !(sig > 4.0 * (double)eps32 * Gd(do_add ? j : 0, do_add ? j : 0));
-        if (do_add && degen) {
-          // degenerate regressor (sklearn _least_angle.py:723-742): covariance zeroed, atom stays inactive
-          status |= 1;
+        if (sizeof(T) == 4 && G64 == nullptr) degen = degen || !(sig > 4.0 * 1.1920928955078125e-07 * Gd(do_add ? j : 0, do_add ? j : 0));
+        // degenerate regressor (sklearn _least_angle.py:723-742): covariance zeroed, atom stays inactive;
+        // otherwise the atom turns active (cov = -inf)
+        if (do_add) {
+          const T cnew = degen ? T(0) : -Num<T>::inf();
 #pragma unroll
           for (int m = 0; m < NA; ++m)
-            if (atom_of(m) == j) cov[m] = T(0);
+            if (atom_of(m) == j) cov[m] = cnew;
+        }
+        if (do_add && degen) {
+          status |= 1;
           do_add = false;
           skip = true;
         }
@@ -494,9 +518,6 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
             }
           }
           sw += tau * (1.0 - su);
-#pragma unroll
-          for (int m = 0; m < NA; ++m)
-            if (atom_of(m) == j) cov[m] = -Num<T>::inf();
           ++n_act;
           max_act = n_act > max_act ? n_act : max_act;
         }
