@@ -273,6 +273,32 @@ def run_ours(args):
         return r
 
     _lib.lasso_lars = timed_lars
+    # optional timeline (analysis only): device timestamps of the side-stream kernels relative to the timed region start
+    tl = []
+    if args.timeline:
+        import torch.distributed as _d
+
+        def wrap(mod, name, label, stream_of):
+            orig = getattr(mod, name)
+
+            def f(*a, **kw):
+                st = stream_of(kw)
+                e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0_.record(st)
+                r = orig(*a, **kw)
+                e1_.record(st)
+                tl.append((label, e0_, e1_))
+                return r
+            setattr(mod, name, f)
+            return orig
+        cur = lambda kw: kw.get("stream") or torch.cuda.current_stream(dev)
+        origs = [(_lib, "update_dict", wrap(_lib, "update_dict", "bcd", cur)),
+                 (_lib, "gram_f64", wrap(_lib, "gram_f64", "gram", cur)),
+                 (_lib, "surrogate_blend", wrap(_lib, "surrogate_blend", "blend", cur)),
+                 (_lib, "cov_tc", wrap(_lib, "cov_tc", "cov", cur)),
+                 (_lib, "surrogate_partial_tc", wrap(_lib, "surrogate_partial_tc", "surrogate", cur))]
+        if world > 1:
+            origs.append((_d, "all_reduce", wrap(_d, "all_reduce", "allreduce", lambda kw: torch.cuda.current_stream(dev))))
     barrier()
     ev0.record(main)
     for _ in range(K):
@@ -282,6 +308,17 @@ def run_ours(args):
     ev1.record(main)
     barrier()
     _lib.lasso_lars = orig_lars
+    if args.timeline:
+        for mod, name, orig in origs:
+            setattr(mod, name, orig)
+        torch.cuda.synchronize(dev)
+        if rank == 0:
+            rows = [(lab, ev0.elapsed_time(a_), ev0.elapsed_time(b_)) for lab, a_, b_ in tl]
+            rows += [("lars", ev0.elapsed_time(a_), ev0.elapsed_time(b_)) for a_, b_ in lars_ev]
+            rows.sort(key=lambda r: r[1])
+            sys.stderr.write("timeline (ms from the start of the timed region): label start end\n")
+            for lab, t0_, t1_ in rows[:80]:
+                sys.stderr.write("  %-10s %8.3f %8.3f\n" % (lab, t0_, t1_))
     clocks = sampler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
     lars_ms = float(np.mean([a.elapsed_time(b) for a, b in lars_ev]))
@@ -394,6 +431,7 @@ def main():
     ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes of the CPU baseline (default: all host cores)")
     ap.add_argument("--batch", type=int, default=0, help="override the global minibatch size (analysis only; the line says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", action="store_true", help="print device timestamps of the step's kernels (analysis only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -924,7 +924,10 @@ static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaSt
 static size_t ws_list_bytes(long long n) { return round_up<size_t>((size_t)n * sizeof(long long), 256); }
 static size_t ws_gp_bytes(int k, int kp) { return round_up<size_t>((size_t)k * kp * sizeof(double), 256); }
 // hybrid first tier (k > 128): 64 slots, the first 40 rows of the packed inverse in shared memory, rows 40..63 here
-constexpr int HYB_SLOTS = 64, HYB_SPLIT = 40;
+#ifndef LARS_HYB_SPLIT
+#define LARS_HYB_SPLIT 40
+#endif
+constexpr int HYB_SLOTS = 64, HYB_SPLIT = LARS_HYB_SPLIT;
 static size_t ws_hyb_bytes(int kp) {
   if (kp <= 128) return 0;
   size_t per = (size_t)(HYB_SLOTS * (HYB_SLOTS + 1) / 2 - HYB_SPLIT * (HYB_SPLIT + 1) / 2) * sizeof(double);

@@ -17,6 +17,7 @@ memory, streams, events and the process group.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -75,10 +76,13 @@ class OnmfEngine:
         self.side = torch.cuda.Stream(dev, priority=-1)     # dictionary update / all-reduce: short kernels, scheduled first
         self._ws_gram = torch.empty(_lib.gram_f64_workspace(d, k), dtype=torch.uint8, device=dev)
         self._ws_gram_s = torch.empty(_lib.gram_f64_workspace(d, k), dtype=torch.uint8, device=dev)  # sparse_code(foreign W)
+        if reserve_sms is None and os.environ.get("ONMF_RESERVE_SMS"):
+            reserve_sms = int(os.environ["ONMF_RESERVE_SMS"])
         self.reserve_sms = reserve_sms
         self._ev_P = torch.cuda.Event()        # P[cur] complete on main
         self._ev_W = torch.cuda.Event()        # W (for the next coding) complete on side
         self._ev_code = torch.cuda.Event()     # main finished reading W / Xt of the current step
+        self._ev_AB = torch.cuda.Event()       # A, B of the previous step blended on side (the next dictionary update follows)
         self._cur = 0
         self.launches = 0
 
@@ -212,6 +216,13 @@ class OnmfEngine:
                 # The coder is a persistent kernel that owns every SM it runs on.  When it is short (few columns per
                 # GPU) the dictionary update on the side stream would otherwise queue behind it and land on the critical
                 # path; leaving one cluster's worth of SMs free lets the two overlap (costs the coder 8/148 of its rate).
+                if self.world > 1:
+                    # The dictionary update is one thread-block cluster: it can only be placed while a whole group of SMs
+                    # in one GPC is free, i.e. BEFORE the persistent coder has spread over the GPU (the SMs the coder leaves
+                    # free are scattered).  On one GPU it is queued at the start of the step and wins that race; across
+                    # GPUs it waits for the all-reduce of the previous partial sums, so hold the coder back until that has
+                    # landed: both become runnable together and the high-priority side stream is placed first.
+                    main.wait_event(self._ev_AB)
                 rsv = self.reserve_sms if self.reserve_sms is not None else (8 if n * self.k <= 131072 * 256 else 0)
                 _lib.set_option(_lib.OPT_LARS_RESERVED_SMS, rsv)
                 _lib.lasso_lars(self.G, Ct, self.d, self.alpha, Ht, self._ws_lars, max_iter=self.max_iter,
@@ -249,6 +260,7 @@ class OnmfEngine:
                     dist.all_reduce(self.P2, group=self.pg)
             _lib.surrogate_blend(self.P[cur], w, self.A, self.B, stream=side)
             self.launches += 1
+            self._ev_AB.record(side)
             if self.track_C:
                 _lib.axpby(w, self.P2, 1.0 - w, self.C, stream=side)
                 self.launches += 1
