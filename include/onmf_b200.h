@@ -155,6 +155,12 @@ int onmf_xxt_partial(int dtype, const void* Xt, int64_t n, int d, void* P2, void
                      size_t workspace_bytes, void* stream);
 int onmf_axpby(int dtype, int64_t count, double a, const void* x, double b, void* y, void* stream);
 
+/* surrogate loss read-out (the error curve of ising_reconstruction.py:133,164 and
+ * network_reconstruction_nx.py): out3[0] = tr(W A W^T) (as <G64, A> with the FP64 Gram of W), out3[1] = tr(W B),
+ * out3[2] = tr(C) (0 when C is NULL); the loss is out3[0] - 2 out3[1] + out3[2].  out3: 3 device doubles. */
+int onmf_surrogate_error(int dtype, const void* W, const double* G64, const void* A, const void* B, const void* C,
+                         int d, int k, double* out3, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2 / K4 on the tensor cores (fp32 only): TMA-fed tcgen05.mma kind::tf32 with TMEM accumulators and a
  * 3xTF32 operand split (hi = rna_tf32(x), lo = x - hi; hi*hi + hi*lo + lo*hi) for fp32-class accuracy.
@@ -190,6 +196,11 @@ int onmf_update_dict(int dtype, const void* W_in, const void* A, const void* B, 
  * ------------------------------------------------------------------------------------------- */
 int onmf_pgd_sweep(int dtype, const void* G, const void* Ct, int64_t n, int k, double alpha,
                    int it, void* Ht, void* stream);
+/* the same sweep restricted to the rows q_begin <= q < q_end of H (atoms): lets the host apply the reference's radius
+ * projection (src/onmf.py:260-262), which -- because of the aliasing `H0 = H1` at :263 -- only ever acts after row 0 of
+ * the first outer iteration. */
+int onmf_pgd_sweep_rows(int dtype, const void* G, const void* Ct, int64_t n, int k, double alpha, int it, void* Ht,
+                        int q_begin, int q_end, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * batched reconstruction: replaces the per-patch Python loop

@@ -63,6 +63,8 @@ SIGNATURES = {
     "onmf_surrogate_partial_tc": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _vp]),
     "onmf_update_dict": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "onmf_pgd_sweep": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _vp, _vp]),
+    "onmf_pgd_sweep_rows": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _vp, _i, _i, _vp]),
+    "onmf_surrogate_error": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "onmf_pgd_code_columns": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _dbl, _vp, _vp]),
     "onmf_patch_grid_mean": (_i, [_i, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "onmf_motif_patches": (_i, [_i, _vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
@@ -252,6 +254,26 @@ def update_dict(W, A, B, W_out, stream=None):
     d, k = W.shape
     _check(load().onmf_update_dict(dt(W), _ptr(W), _ptr(A), _ptr(B), d, k, _ptr(W_out), _stream(stream)), "onmf_update_dict")
     return W_out
+
+
+def surrogate_error(W, G64, A, B, C, out3, stream=None):
+    """out3 (3 float64 on the device) = [tr(W A W^T), tr(W B), tr(C)]."""
+    _req(W, "W"); _req(G64, "G64", torch.float64); _req(A, "A", W.dtype); _req(B, "B", W.dtype)
+    _req(out3, "out3", torch.float64)
+    if C is not None:
+        _req(C, "C", W.dtype)
+    d, k = W.shape
+    _check(load().onmf_surrogate_error(dt(W), _ptr(W), _ptr(G64), _ptr(A), _ptr(B), _ptr(C), d, k, _ptr(out3),
+                                       _stream(stream)), "onmf_surrogate_error")
+    return out3
+
+
+def pgd_sweep_rows(G, Ct, alpha, it, Ht, q_begin, q_end, stream=None):
+    _req(G, "G"); _req(Ct, "Ct", G.dtype); _req(Ht, "Ht", G.dtype)
+    n, k = Ct.shape
+    _check(load().onmf_pgd_sweep_rows(dt(G), _ptr(G), _ptr(Ct), n, k, float(alpha), int(it), _ptr(Ht), int(q_begin),
+                                      int(q_end), _stream(stream)), "onmf_pgd_sweep_rows")
+    return Ht
 
 
 def pgd_sweep(G, Ct, alpha, it, Ht, stream=None):

@@ -62,7 +62,7 @@ __global__ void transpose_kernel(const TI* __restrict__ src, long long rows, lon
 // independently per sample.  One warp per sample; h lives in registers (atom i on lane i%32).
 template <typename T, int NA>
 __global__ void pgd_sweep_kernel(const T* __restrict__ G, const T* __restrict__ Ct, long long n, int k, T alpha, T scale,
-                                 T* __restrict__ Ht) {
+                                 T* __restrict__ Ht, int q_begin, int q_end) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Gs = reinterpret_cast<T*>(smem_raw);
   for (int i = threadIdx.x; i < k * k; i += blockDim.x) Gs[i] = G[i];
@@ -77,7 +77,7 @@ __global__ void pgd_sweep_kernel(const T* __restrict__ G, const T* __restrict__ 
       int i = lane + 32 * m;
       h[m] = i < k ? Ht[(size_t)j * k + i] : T(0);
     }
-    for (int q = 0; q < k; ++q) {
+    for (int q = q_begin; q < q_end; ++q) {
       T part = T(0);
 #pragma unroll
       for (int m = 0; m < NA; ++m) {
@@ -215,7 +215,8 @@ __global__ void patch_grid_mean_kernel(const T* __restrict__ R, long long ldr, i
 }
 
 template <typename T>
-static int pgd_t(const T* G, const T* Ct, long long n, int k, double alpha, int it, T* Ht, cudaStream_t st) {
+static int pgd_t(const T* G, const T* Ct, long long n, int k, double alpha, int it, T* Ht, int q_begin, int q_end,
+                 cudaStream_t st) {
   size_t smem = (size_t)k * k * sizeof(T);
   if (smem > (size_t)max_smem_optin()) return fail(ONMF_E_UNSUPPORTED, "pgd_sweep: Gram does not fit in shared memory");
   const T scale = (T)sqrt((double)it + 10.0);
@@ -228,7 +229,7 @@ static int pgd_t(const T* G, const T* Ct, long long n, int k, double alpha, int 
   {                                                                                                  \
     auto kern = pgd_sweep_kernel<T, NA>;                                                             \
     ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    kern<<<grid, threads, smem, st>>>(G, Ct, n, k, (T)alpha, scale, Ht);                             \
+    kern<<<grid, threads, smem, st>>>(G, Ct, n, k, (T)alpha, scale, Ht, q_begin, q_end);             \
   }
   if (k <= 32) ONMF_PGD(1)
   else if (k <= 64) ONMF_PGD(2)
@@ -299,13 +300,24 @@ extern "C" int onmf_transpose(int dtype_in, int dtype_out, const void* src, int6
   return fail(ONMF_E_ARG, "transpose: bad dtype");
 }
 
+extern "C" int onmf_pgd_sweep_rows(int dtype, const void* G, const void* Ct, int64_t n, int k, double alpha, int it, void* Ht,
+                                   int q_begin, int q_end, void* stream) {
+  if (!G || !Ct || !Ht || n < 0 || k <= 0 || it < 0 || q_begin < 0 || q_end > k || q_begin > q_end)
+    return fail(ONMF_E_ARG, "pgd_sweep_rows: bad argument");
+  if (n == 0 || q_begin == q_end) return ONMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == ONMF_F32) return pgd_t<float>((const float*)G, (const float*)Ct, n, k, alpha, it, (float*)Ht, q_begin, q_end, st);
+  if (dtype == ONMF_F64) return pgd_t<double>((const double*)G, (const double*)Ct, n, k, alpha, it, (double*)Ht, q_begin, q_end, st);
+  return fail(ONMF_E_ARG, "pgd_sweep_rows: bad dtype");
+}
+
 extern "C" int onmf_pgd_sweep(int dtype, const void* G, const void* Ct, int64_t n, int k, double alpha, int it, void* Ht,
                               void* stream) {
   if (!G || !Ct || !Ht || n < 0 || k <= 0 || it < 0) return fail(ONMF_E_ARG, "pgd_sweep: bad argument");
   if (n == 0) return ONMF_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == ONMF_F32) return pgd_t<float>((const float*)G, (const float*)Ct, n, k, alpha, it, (float*)Ht, st);
-  if (dtype == ONMF_F64) return pgd_t<double>((const double*)G, (const double*)Ct, n, k, alpha, it, (double*)Ht, st);
+  if (dtype == ONMF_F32) return pgd_t<float>((const float*)G, (const float*)Ct, n, k, alpha, it, (float*)Ht, 0, k, st);
+  if (dtype == ONMF_F64) return pgd_t<double>((const double*)G, (const double*)Ct, n, k, alpha, it, (double*)Ht, 0, k, st);
   return fail(ONMF_E_ARG, "pgd_sweep: bad dtype");
 }
 

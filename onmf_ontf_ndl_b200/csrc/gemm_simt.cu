@@ -264,6 +264,47 @@ static int gram64_splits(int d) {
   return s < 1 ? 1 : s > 16 ? 16 : s;
 }
 
+// surrogate loss read-out  tr(W A W^T) - 2 tr(W B) + tr(C)  (reference ising_reconstruction.py:133,164):
+//   out[0] = <W^T W, A> = tr(W A W^T)   (the FP64 Gram of W is already maintained for the coder)
+//   out[1] = tr(W B) = sum_{r,j} W[r,j] B[j,r]        out[2] = tr(C)
+// One CTA, FP64 accumulation, fixed summation order (deterministic); the three sums are ~3e5 terms at cfg5.
+template <typename T>
+__global__ void __launch_bounds__(1024) surrogate_error_kernel(const T* __restrict__ W, const double* __restrict__ G64,
+                                                               const T* __restrict__ A, const T* __restrict__ B,
+                                                               const T* __restrict__ C, int d, int k, double* __restrict__ out) {
+  __shared__ double red[3][32];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < k * k; i += blockDim.x) s0 += G64[i] * (double)A[i];
+  for (long long i = threadIdx.x; i < (long long)d * k; i += blockDim.x) {
+    const int j = (int)(i / d), r = (int)(i - (long long)j * d);          // B is (k x d): coalesced along r
+    s1 += (double)B[i] * (double)W[(size_t)r * k + j];
+  }
+  if (C != nullptr)
+    for (int i = threadIdx.x; i < d; i += blockDim.x) s2 += (double)C[(size_t)i * d + i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; red[2][warp] = s2; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) / 32;
+    s0 = lane < nw ? red[0][lane] : 0.0;
+    s1 = lane < nw ? red[1][lane] : 0.0;
+    s2 = lane < nw ? red[2][lane] : 0.0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    if (lane == 0) { out[0] = s0; out[1] = s1; out[2] = s2; }
+  }
+}
+
 }  // namespace onmf
 
 using namespace onmf;
@@ -412,5 +453,19 @@ extern "C" int onmf_axpby(int dtype, int64_t count, double a, const void* x, dou
   else if (dtype == ONMF_F64) axpby_kernel<double><<<grid, 256, 0, st>>>(count, a, (const double*)x, b, (double*)y);
   else return fail(ONMF_E_ARG, "axpby: bad dtype");
   ONMF_LAUNCH_CHECK("axpby_kernel");
+  return ONMF_OK;
+}
+
+extern "C" int onmf_surrogate_error(int dtype, const void* W, const double* G64, const void* A, const void* B, const void* C,
+                                    int d, int k, double* out3, void* stream) {
+  if (!W || !G64 || !A || !B || !out3 || d <= 0 || k <= 0) return fail(ONMF_E_ARG, "surrogate_error: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == ONMF_F32)
+    surrogate_error_kernel<float><<<1, 1024, 0, st>>>((const float*)W, G64, (const float*)A, (const float*)B, (const float*)C, d, k, out3);
+  else if (dtype == ONMF_F64)
+    surrogate_error_kernel<double><<<1, 1024, 0, st>>>((const double*)W, G64, (const double*)A, (const double*)B, (const double*)C, d, k, out3);
+  else
+    return fail(ONMF_E_ARG, "surrogate_error: bad dtype");
+  ONMF_LAUNCH_CHECK("surrogate_error_kernel");
   return ONMF_OK;
 }

@@ -314,6 +314,16 @@ class OnmfEngine:
         self.flush()
         return self.W, self.A, self.B, self.C
 
+    def surrogate_error(self):
+        """tr(W A W^T) - 2 tr(W B) + tr(C): the surrogate loss the Ising / network drivers plot
+        (ising_reconstruction.py:133,164); tr(C) is included when the engine tracks C.  Returns a float."""
+        self.flush()
+        out = torch.empty(3, dtype=torch.float64, device=self.device)
+        _lib.surrogate_error(self.W, self.G, self.A, self.B, self.C, out)
+        self.launches += 1
+        t = out.cpu().tolist()
+        return t[0] - 2.0 * t[1] + t[2]
+
     def read_stats(self):
         torch.cuda.synchronize(self.device)
         vals = self.stats.cpu().tolist()

@@ -205,10 +205,16 @@ def _spectral_norm(M):
     return torch.linalg.matrix_norm(M, ord=2)
 
 
-def _pgd_device(Xt, Wd, Ht, alpha, sub_iter, stopping_diff):
-    """Outer loop of the reference's projected-gradient coder (src/onmf.py:252-268, r=None) around the
-    onmf_pgd_sweep kernel.  The stopping test needs two spectral norms per outer iteration
-    (np.linalg.norm(., 2), src/onmf.py:265); they are taken with torch.linalg on the device."""
+def _pgd_device(Xt, Wd, Ht, alpha, sub_iter, stopping_diff, r=None):
+    """Outer loop of the reference's projected-gradient coder (src/onmf.py:252-268) around the onmf_pgd_sweep
+    kernel.  The stopping test needs two spectral norms per outer iteration (np.linalg.norm(., 2),
+    src/onmf.py:265); they are taken with torch.linalg on the device.
+
+    Radius mode (r is not None, src/onmf.py:260-263): the reference projects H1 back to within spectral distance r of
+    H0 after every row update and then executes `H0 = H1`, which ALIASES the two arrays -- from the second row on the
+    in-place row updates change H0 as well, the distance is 0 and the projection is the identity.  So the projection
+    acts exactly once: after row 0 of the first outer iteration, where H1 - H0 has a single non-zero row and its
+    spectral norm is that row's 2-norm.  Reproduced literally (golden vector tests/golden/pgd_coder.npz:H_radius)."""
     k = Wd.shape[1]
     G = torch.empty(k, k, dtype=Wd.dtype, device=Wd.device)
     Ct = torch.empty(Xt.shape[0], k, dtype=Wd.dtype, device=Wd.device)
@@ -217,7 +223,15 @@ def _pgd_device(Xt, Wd, Ht, alpha, sub_iter, stopping_diff):
     i, dist = 0, 1.0
     while i < sub_iter and dist > stopping_diff:
         H_old = Ht.clone()
-        _lib.pgd_sweep(G, Ct, alpha, i, Ht)
+        if r is not None and i == 0:
+            h_before = Ht[:, 0].clone()                          # row 0 of H = column 0 of the sample-major Ht
+            _lib.pgd_sweep_rows(G, Ct, alpha, i, Ht, 0, 1)
+            delta = Ht[:, 0] - h_before
+            dd = float(torch.linalg.vector_norm(delta))
+            Ht[:, 0] = h_before + (r / max(r, dd)) * delta
+            _lib.pgd_sweep_rows(G, Ct, alpha, i, Ht, 1, k)
+        else:
+            _lib.pgd_sweep(G, Ct, alpha, i, Ht)
         dist = float(_spectral_norm(Ht - H_old) / _spectral_norm(H_old))
         i += 1
     return Ht
@@ -226,9 +240,8 @@ def _pgd_device(Xt, Wd, Ht, alpha, sub_iter, stopping_diff):
 def update_code_within_radius(X, W, H0=None, r=None, alpha=0, sub_iter=10, stopping_diff=0.1, precision=None):
     """Row-wise projected gradient descent for argmin_H |X - WH|^2/2 + alpha|H|_1, H >= 0
     (reference src/onmf.py:233-271).  Returns H (r x n) as numpy float64."""
-    if r is not None:
-        raise NotImplementedError("radius-restricted coding (r is not None) is not on the B200 hot path; "
-                                  "no shipped driver uses it (image_reconstruction.py:384 passes r=None)")
+    if r is not None and not (r > 0):
+        raise ValueError("r must be positive (the reference divides by max(r, distance) and returns NaN for r = 0)")
     dev = _host.device()
     dtype = _host.torch_dtype(precision)
     X = np.asarray(X)
@@ -238,5 +251,5 @@ def update_code_within_radius(X, W, H0=None, r=None, alpha=0, sub_iter=10, stopp
     Xt = _host.to_sample_major(X, dtype, dev)
     Wd = _host.to_device(W, dtype, dev)
     Ht = _host.to_device(np.ascontiguousarray(np.asarray(H0).T), dtype, dev)
-    Ht = _pgd_device(Xt, Wd, Ht, alpha, sub_iter, stopping_diff)
+    Ht = _pgd_device(Xt, Wd, Ht, alpha, sub_iter, stopping_diff, r=r)
     return _host.from_sample_major(Ht)

@@ -284,8 +284,14 @@ def test_pgd_coder_and_shipped_compat(golden_dir):
     H1 = update_code_within_radius(g["X"][:, :1], g["W"], H0=g["H0"][:, :1], r=None, alpha=1, sub_iter=10,
                                    stopping_diff=0.01, precision="fp64")
     assert rel(H1, g["H_single"]) < 1e-9
-    with pytest.raises(NotImplementedError):
-        update_code_within_radius(g["X"], g["W"], H0=g["H0"], r=0.5)
+    # radius mode (src/onmf.py:260-263 incl. the H0 = H1 aliasing): the reference's own output
+    Hr = update_code_within_radius(g["X"], g["W"], H0=g["H0"], r=0.5, alpha=0.3, sub_iter=3, stopping_diff=0.01,
+                                   precision="fp64")
+    assert rel(Hr, g["H_radius"]) < 1e-9
+    Hr32 = update_code_within_radius(g["X"], g["W"], H0=g["H0"], r=0.5, alpha=0.3, sub_iter=3, stopping_diff=0.01)
+    assert rel(Hr32, g["H_radius"]) < 1e-4
+    with pytest.raises(ValueError):
+        update_code_within_radius(g["X"], g["W"], H0=g["H0"], r=0.0)
     s = load(golden_dir, "shipped_onmf")                     # literal shipped src/onmf.py run, seed 71
     np.random.seed(int(s["seed"]))
     m = Online_NMF(s["X"], n_components=25, iterations=4, batch_size=60, alpha=1, subsample=True, compat="shipped_onmf",
@@ -535,3 +541,27 @@ def test_fp32_near_tie_column_and_fp64_gram(golden_dir):
         assert np.abs(G.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
         assert torch.equal(G, G.T.contiguous())
         assert np.array_equal(G32.cpu().numpy(), G.cpu().numpy().astype(np.float32))
+
+
+def test_surrogate_error_readout(golden_dir):
+    """tr(W A W^T) - 2 tr(W B) + tr(C) (ising_reconstruction.py:133,164) from the engine's resident state vs the oracle."""
+    g = load(golden_dir, "cfg4_ising_pm1")
+    X = g["X"]
+    d = X.shape[0]
+    k = int(g["W0"].shape[1]) if "W0" in g else 12
+    rng = np.random.default_rng(3)
+    W0 = g["W0"] if "W0" in g else rng.random((d, k))
+    for dt_, tol in ((torch.float64, 1e-10), (torch.float32, 1e-4)):
+        eng = OnmfEngine(d, k, alpha=1.0, dtype=dt_, device=dev(), track_C=True, use_tc=False)
+        eng.set_state(W0)
+        Xt = tt(X.T, dt_)
+        A, B, C, W = np.zeros((k, k)), np.zeros((k, d)), np.zeros((d, d)), W0
+        for t in (1, 2, 3):
+            eng.step(Xt, float(t))
+            H, A1, B1, W1 = c_oracle.step(X, A, B, W, float(t), 1.0)
+            C = (1 - 1.0 / t) * C + (1.0 / t) * (X @ X.T)
+            A, B, W = A1, B1, W1
+        ref = O.surrogate_error(W, A, B, C)
+        got = eng.surrogate_error()
+        scale = abs(np.trace(C)) + abs(ref)
+        assert abs(got - ref) <= tol * scale, (got, ref)
