@@ -380,7 +380,7 @@ def run_ours(args):
                 "unit": "GB/s", "frac": achieved / hbm_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one tier-0 launch at cfg5, N=1 (ncu --set full,
                 # profiles/r1_lars_k256_ncu.md); only valid for that workload
-                "traffic": 4.95e8 if (args.workload == "cfg5" and world == 1) else None, "peak_source": peak_src,
+                "traffic": 4.94e8 if (args.workload == "cfg5" and world == 1) else None, "peak_source": peak_src,
                 "ms_per_launch": lars_ms, "share_of_step": lars_ms * K / elapsed_ms,
                 "note": "the coder is FP32-FMA / shared-memory bound, not HBM bound; see lars_work"}
     lars_work = {"knots_per_column": stats["knots"] / cols, "mean_active": stats["sum_active"] / max(stats["knots"], 1),
