@@ -42,9 +42,6 @@
 
 namespace onmf {
 
-#ifndef LARS_PREFETCH
-#define LARS_PREFETCH 0
-#endif
 #ifndef LARS_MAX_THREADS
 #define LARS_MAX_THREADS 512     // 16 warps/SM at <= 128 registers per thread (20 warps at 96 registers measured no faster)
 #endif
@@ -122,6 +119,20 @@ __device__ __forceinline__ void gargmax(double& v, int& i, unsigned) {
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
   }
 }
+// group maximum (fp32: one REDUX on the order-preserving key)
+template <int LPC>
+__device__ __forceinline__ float gmaxval(float v, unsigned gmask) {
+  return fkey_inv(__reduce_max_sync(gmask, fkey(v)));
+}
+template <int LPC>
+__device__ __forceinline__ double gmaxval(double v, unsigned) {
+#pragma unroll
+  for (int off = LPC / 2; off > 0; off >>= 1) {
+    double o = __shfl_xor_sync(0xffffffffu, v, off);
+    v = o > v ? o : v;
+  }
+  return v;
+}
 // min over strictly positive candidates (callers pass big() for "none")
 template <int LPC>
 __device__ __forceinline__ float gminpos(float v, unsigned gmask) {
@@ -167,6 +178,11 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   y = y * (1.5 - 0.5 * x * y * y);
   y = y * (1.5 - 0.5 * x * y * y);
   return y;
+}
+// one Newton step: ~1e-13 relative, enough where the result is rounded to fp32 anyway
+__device__ __forceinline__ double fast_rsqrt1(double x) {
+  double y = (double)rsqrtf((float)x);
+  return y * (1.5 - 0.5 * x * y * y);
 }
 __device__ __forceinline__ float qdiv(float a, float b) {      // step-length candidates: a * rcp.approx(b), 2 instructions
   float r;
@@ -369,7 +385,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
       if (LPC * m < sW) {
         const int p = l + LPC * m;
         double gv = 0.0;
-        if (on && p < s) gv = Gd(acts[p], a);
+        if (on && p < s) gv = Gd(a, acts[p]);      // row a of the (bitwise symmetric) Gram: one 8k-byte region for all lanes
         gs[p] = gv;
       }
     }
@@ -440,12 +456,23 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
       // ---- 1. largest inactive covariance ----
       T best = -Num<T>::inf();
       int bi = 0x7fffffff;
+      if (sizeof(T) == 4) {
+        // value first (FMNMX + one REDUX), then the lowest atom attaining it (atom_of(m) increases with m)
 #pragma unroll
-      for (int m = 0; m < NA; ++m) {
-        const int i = atom_of(m);
-        if (cov[m] > best || (cov[m] == best && i < bi)) { best = cov[m]; bi = i; }
+        for (int m = 0; m < NA; ++m) best = cov[m] > best ? cov[m] : best;
+        best = gmaxval<LPC>(best, gmask);
+#pragma unroll
+        for (int m = NA - 1; m >= 0; --m)
+          if (cov[m] == best) bi = atom_of(m);
+        bi = __reduce_min_sync(gmask, bi);
+      } else {
+#pragma unroll
+        for (int m = 0; m < NA; ++m) {
+          const int i = atom_of(m);
+          if (cov[m] > best || (cov[m] == best && i < bi)) { best = cov[m]; bi = i; }
+        }
+        gargmax<LPC>(best, bi, gmask);
       }
-      gargmax<LPC>(best, bi, gmask);
       const bool any_inact = best > -Num<T>::inf();
       const T C = any_inact ? best : T(0);
       // recorded alpha of the knot = C / d (sklearn divides by n_samples).  The fp32 coder keeps it in covariance units
@@ -538,7 +565,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         live = false;
       }
       const int hwL = __reduce_max_sync(0xffffffffu, live ? n_act : 0);
-      const double AAd = live ? fast_rsqrt(sw) : 1.0;
+      const double AAd = live ? ((sizeof(T) == 4) ? fast_rsqrt1(sw) : fast_rsqrt(sw)) : 1.0;
       const T AA = (T)AAd;
       T w[SA];
 #pragma unroll

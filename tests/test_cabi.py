@@ -69,3 +69,20 @@ def test_product_never_imports_oracle():
             txt = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in txt.replace("# oracle", ""), fn
             assert "sklearn" not in txt.split('"""')[-1], fn
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """bench.py --impl reference: the CPU arm (oracle port of the reference's numpy + sklearn step) on a tiny bounded
+    sample, two worker processes; one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "cfg1",
+                          "--steps", "1", "--warmup", "0", "--cpu-cols", "64", "--cpu-procs", "2"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
+    assert line["cpu_baseline"]["cores"] == 2 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
