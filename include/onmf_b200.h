@@ -221,6 +221,66 @@ int onmf_patch_grid_mean(int dtype, const void* R, int64_t ldr, int ny, int nx, 
 int onmf_motif_patches(int dtype, const int64_t* rowptr, const int32_t* colidx, int n_nodes, const int32_t* emb,
                        int64_t n, int kk, void* Xt, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The fused online step: ONE host call per minibatch
+ * replaces: Online_NTF.step / Online_NMF.step  (src/ontf.py:117-154, src/onmf.py:119-167) -- sparse_code, the A/B
+ *           recursion and update_dict with the OLD aggregates -- as a fixed schedule of the kernels above on two
+ *           streams (DESIGN.md "Step schedule").  The plan owns the CUDA events that order the streams; the caller owns
+ *           every buffer.  Nothing here allocates device memory or synchronises the host.
+ *   single GPU : onmf_step(plan, buffers, Xt, NULL, n, w, cur)
+ *   multi GPU  : onmf_step_launch(...);  all-reduce(sum) P[cur] (and P2) on side_stream;  onmf_step_finish(..., w, cur)
+ * `cur` (0/1) selects the current dictionary W[cur] (with G[cur], Whi/Wlo[cur]) and the partial-sum buffer P[cur]; the
+ * step writes the new dictionary to index cur^1 and the caller flips cur afterwards.  w = t^-beta.
+ * Xt (n x d) are this rank's columns; Xt = NULL (tensor-core path): Xhi/Xlo already hold the split minibatch.
+ * codes != NULL: externally computed codes (n x k) are aggregated instead of running the coder.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct onmf_step_plan onmf_step_plan;
+typedef struct {
+  int dtype, d, k;
+  int use_tc;            /* tensor-core products (fp32, onmf_tc_supported(k, d)) */
+  int track_C;           /* also maintain C <- (1-w) C + w X X^T (src/onmf.py:157-158) */
+  int max_iter;          /* LARS iteration cap (sklearn: 1000) */
+  int reserve_sms;       /* SMs the coder leaves free for the dictionary update; -1 = automatic */
+  int hold_coder;        /* 1: the coder waits for the previous step's blend (multi-GPU) */
+  double alpha;
+  void* W[2];            /* d x k */
+  double* G[2];          /* k x k, FP64 Gram of W[i] (always FP64) */
+  void* Whi[2];          /* TF32 split of W[i] (tensor-core path) */
+  void* Wlo[2];
+  void* A;               /* k x k */
+  void* B;               /* k x d */
+  void* C;               /* d x d or NULL */
+  void* P[2];            /* k x (k+d) packed partial sums, double-buffered */
+  void* P2;              /* d x d partial sum for C or NULL */
+  void* Ct;              /* n x k covariances */
+  void* Ht;              /* n x k codes (output) */
+  void* Xhi;             /* n x d TF32 split of the minibatch (tensor-core path) */
+  void* Xlo;
+  void* Hhi;             /* n x k TF32 split of the codes */
+  void* Hlo;
+  void* ws_lars;  size_t ws_lars_bytes;   /* onmf_lasso_lars_workspace, zero-filled once */
+  void* ws_sur;   size_t ws_sur_bytes;    /* max(onmf_surrogate_workspace, onmf_surrogate_tc_workspace[, xxt]) */
+  void* ws_gram;  size_t ws_gram_bytes;   /* onmf_gram_f64_workspace */
+  onmf_lars_stats* stats;                 /* or NULL */
+  void* main_stream;
+  void* side_stream;
+} onmf_step_buffers;
+
+/* timing_slots > 0: the plan keeps a ring of event pairs around the coder launch (read with onmf_step_plan_lars_ms) */
+int onmf_step_plan_create(onmf_step_plan** plan, int timing_slots);
+int onmf_step_plan_destroy(onmf_step_plan* plan);
+/* call after (re)setting W, A, B on main_stream: the first dictionary update must wait for those writes */
+int onmf_step_plan_mark_state(onmf_step_plan* plan, void* main_stream);
+long long onmf_step_plan_launches(const onmf_step_plan* plan);    /* kernels launched through the plan so far */
+int onmf_step_plan_reset_timing(onmf_step_plan* plan);
+/* elapsed ms of the coder launch of the last (up to timing_slots) steps; waits for those launches to finish */
+int onmf_step_plan_lars_ms(onmf_step_plan* plan, float* out, int max_out, int* n_out);
+int onmf_step_launch(onmf_step_plan* plan, const onmf_step_buffers* b, const void* Xt, const void* codes, int64_t n,
+                     int cur);
+int onmf_step_finish(onmf_step_plan* plan, const onmf_step_buffers* b, double w, int cur);
+int onmf_step(onmf_step_plan* plan, const onmf_step_buffers* b, const void* Xt, const void* codes, int64_t n, double w,
+              int cur);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,7 +68,29 @@ SIGNATURES = {
     "onmf_pgd_code_columns": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _dbl, _vp, _vp]),
     "onmf_patch_grid_mean": (_i, [_i, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "onmf_motif_patches": (_i, [_i, _vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "onmf_step_plan_create": (_i, [ctypes.POINTER(_vp), _i]),
+    "onmf_step_plan_destroy": (_i, [_vp]),
+    "onmf_step_plan_mark_state": (_i, [_vp, _vp]),
+    "onmf_step_plan_launches": (ctypes.c_longlong, [_vp]),
+    "onmf_step_plan_reset_timing": (_i, [_vp]),
+    "onmf_step_plan_lars_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float), _i, ctypes.POINTER(_i)]),
+    "onmf_step_launch": (_i, [_vp, _vp, _vp, _vp, _i64, _i]),
+    "onmf_step_finish": (_i, [_vp, _vp, _dbl, _i]),
+    "onmf_step": (_i, [_vp, _vp, _vp, _vp, _i64, _dbl, _i]),
 }
+
+
+
+class StepBuffers(ctypes.Structure):
+    """onmf_step_buffers (include/onmf_b200.h)."""
+    _fields_ = [("dtype", _i), ("d", _i), ("k", _i), ("use_tc", _i), ("track_C", _i), ("max_iter", _i),
+                ("reserve_sms", _i), ("hold_coder", _i), ("alpha", _dbl),
+                ("W", _vp * 2), ("G", _vp * 2), ("Whi", _vp * 2), ("Wlo", _vp * 2),
+                ("A", _vp), ("B", _vp), ("C", _vp), ("P", _vp * 2), ("P2", _vp),
+                ("Ct", _vp), ("Ht", _vp), ("Xhi", _vp), ("Xlo", _vp), ("Hhi", _vp), ("Hlo", _vp),
+                ("ws_lars", _vp), ("ws_lars_bytes", _sz), ("ws_sur", _vp), ("ws_sur_bytes", _sz),
+                ("ws_gram", _vp), ("ws_gram_bytes", _sz), ("stats", _vp), ("main_stream", _vp), ("side_stream", _vp)]
+
 
 _lib = None
 
@@ -351,3 +373,48 @@ def motif_patches(rowptr, colidx, emb, out, stream=None):
     _check(load().onmf_motif_patches(dt(out), _ptr(rowptr), _ptr(colidx), rowptr.shape[0] - 1, _ptr(emb), n, kk, _ptr(out),
                                      _stream(stream)), "onmf_motif_patches")
     return out
+
+
+# ---- fused step (csrc/step.cu) ---------------------------------------------------------------------
+
+class StepPlan:
+    """Owner of an onmf_step_plan (CUDA events ordering the two streams of the fused step)."""
+
+    def __init__(self, timing_slots=0):
+        self._h = _vp()
+        _check(load().onmf_step_plan_create(ctypes.byref(self._h), int(timing_slots)), "onmf_step_plan_create")
+        self.timing_slots = int(timing_slots)
+
+    def __del__(self):
+        try:
+            if self._h:
+                load().onmf_step_plan_destroy(self._h)
+                self._h = _vp()
+        except Exception:
+            pass
+
+    def mark_state(self, main_stream):
+        _check(load().onmf_step_plan_mark_state(self._h, _stream(main_stream)), "onmf_step_plan_mark_state")
+
+    def launches(self):
+        return int(load().onmf_step_plan_launches(self._h))
+
+    def reset_timing(self):
+        _check(load().onmf_step_plan_reset_timing(self._h), "onmf_step_plan_reset_timing")
+
+    def lars_ms(self):
+        if self.timing_slots <= 0:
+            return []
+        buf = (ctypes.c_float * self.timing_slots)()
+        n = _i(0)
+        _check(load().onmf_step_plan_lars_ms(self._h, buf, self.timing_slots, ctypes.byref(n)), "onmf_step_plan_lars_ms")
+        return [float(buf[i]) for i in range(n.value)]
+
+    def launch(self, bufs, Xt, codes, n, cur):
+        _check(load().onmf_step_launch(self._h, ctypes.byref(bufs), _ptr(Xt), _ptr(codes), int(n), int(cur)), "onmf_step_launch")
+
+    def finish(self, bufs, w, cur):
+        _check(load().onmf_step_finish(self._h, ctypes.byref(bufs), float(w), int(cur)), "onmf_step_finish")
+
+    def step(self, bufs, Xt, codes, n, w, cur):
+        _check(load().onmf_step(self._h, ctypes.byref(bufs), _ptr(Xt), _ptr(codes), int(n), float(w), int(cur)), "onmf_step")

@@ -29,7 +29,7 @@ class OnmfEngine:
     def __init__(self, d: int, k: int, alpha: float = 1.0, beta: Optional[float] = None,
                  dtype: torch.dtype = torch.float32, device=None, max_iter: int = 1000,
                  process_group=None, track_C: bool = False, collect_stats: bool = False, use_tc=None,
-                 reserve_sms: Optional[int] = None):
+                 reserve_sms: Optional[int] = None, fused: bool = True):
         if not torch.cuda.is_available():
             raise _lib.OnmfKernelError("OnmfEngine needs a CUDA device (there is no CPU path)")
         _lib.load()
@@ -84,7 +84,60 @@ class OnmfEngine:
         self._ev_code = torch.cuda.Event()     # main finished reading W / Xt of the current step
         self._ev_AB = torch.cuda.Event()       # A, B of the previous step blended on side (the next dictionary update follows)
         self._cur = 0
-        self.launches = 0
+        self._launches_py = 0
+        # fused step (csrc/step.cu): one C call per minibatch enqueues the whole schedule; the Python-composed schedule
+        # below (same kernels, same ordering, torch events) remains for analysis (bench.py --timeline)
+        self.fused = bool(fused)
+        self._plan = _lib.StepPlan(timing_slots=256) if self.fused else None
+        self._pairs = None
+        self._sb = None
+
+    @property
+    def launches(self):
+        """kernels launched so far (Python-composed calls + the fused plan's own count)"""
+        return self._launches_py + (self._plan.launches() if self._plan is not None else 0)
+
+    @launches.setter
+    def launches(self, v):
+        self._launches_py = int(v) - (self._plan.launches() if self._plan is not None else 0)
+
+    def _make_bufs(self):
+        """(re)build the onmf_step_buffers descriptor of the fused step from the engine's tensors"""
+        if self._pairs is None:      # fixed order of the double buffers: index == self._cur
+            tc = self.use_tc
+            self._pairs = dict(W=[self.W, self.W_next], G=[self.G, self.G_next],
+                               Whi=[self.Whi, self.Whi_next] if tc else [None, None],
+                               Wlo=[self.Wlo, self.Wlo_next] if tc else [None, None])
+        p = lambda t: t.data_ptr() if t is not None else None
+        sb = _lib.StepBuffers()
+        sb.dtype = _lib.F64 if self.dtype == torch.float64 else _lib.F32
+        sb.d, sb.k = self.d, self.k
+        sb.use_tc, sb.track_C, sb.max_iter = int(self.use_tc), int(self.track_C), self.max_iter
+        sb.reserve_sms = -1 if self.reserve_sms is None else int(self.reserve_sms)
+        sb.hold_coder = int(self.world > 1)
+        sb.alpha = self.alpha
+        for name in ("W", "G", "Whi", "Wlo"):
+            arr = getattr(sb, name)
+            arr[0], arr[1] = p(self._pairs[name][0]), p(self._pairs[name][1])
+        sb.A, sb.B, sb.C = p(self.A), p(self.B), p(self.C)
+        sb.P[0], sb.P[1] = p(self.P[0]), p(self.P[1])
+        sb.P2 = p(self.P2)
+        sb.Ct, sb.Ht = p(self.Ct), p(self.Ht)
+        sb.Xhi, sb.Xlo, sb.Hhi, sb.Hlo = p(self.Xhi), p(self.Xlo), p(self.Hhi), p(self.Hlo)
+        sb.ws_lars = p(self._ws_lars); sb.ws_lars_bytes = self._ws_lars.numel() if self._ws_lars is not None else 0
+        sb.ws_sur = p(self._ws_sur); sb.ws_sur_bytes = self._ws_sur.numel() if self._ws_sur is not None else 0
+        sb.ws_gram = p(self._ws_gram); sb.ws_gram_bytes = self._ws_gram.numel()
+        sb.stats = p(self.stats)
+        sb.main_stream, sb.side_stream = self.main.cuda_stream, self.side.cuda_stream
+        self._sb = sb
+
+    def reset_lars_timing(self):
+        if self._plan is not None:
+            self._plan.reset_timing()
+
+    def read_lars_ms(self):
+        """elapsed ms of the coder launch of the last steps (fused path; waits for them)"""
+        return self._plan.lars_ms() if self._plan is not None else []
 
     # ------------------------------------------------------------------ state
     def set_state(self, W, A=None, B=None, C=None):
@@ -99,7 +152,10 @@ class OnmfEngine:
                 dst.copy_(torch.as_tensor(src).to(self.device, self.dtype))
         self._derive(self.W, self.G, getattr(self, "Whi", None), getattr(self, "Wlo", None), self.main)
         # the first dictionary update (side stream) reads W, A, B and shares the Gram workspace with the derive above
-        self._ev_code.record(self.main)
+        if self._plan is not None:
+            self._plan.mark_state(self.main)
+        else:
+            self._ev_code.record(self.main)
 
     def _derive(self, W, G, Whi, Wlo, stream, use_ws=True):
         """Everything the coder needs that depends on the dictionary only: Gram matrix and (tensor-core path)
@@ -128,6 +184,7 @@ class OnmfEngine:
             self.Hhi = torch.empty(self._cap, self.k, dtype=dt_, device=dev)
             self.Hlo = torch.empty(self._cap, self.k, dtype=dt_, device=dev)
         self._ws_sur = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._sb = None                       # the fused step's descriptor points at the old buffers
 
     def _stats_ptr(self):
         return self.stats
@@ -188,6 +245,8 @@ class OnmfEngine:
         self._reserve(max(n, 1))
         w = float(t) ** (-self.beta)
         cur = self._cur
+        if self.fused:
+            return self._step_fused(Xt, codes, n, w, cur)
         # side stream: dictionary update for this step with the OLD aggregates (src/ontf.py:151).  It is
         # queued behind the previous step's all-reduce + blend (same stream), and must not overwrite the
         # buffer the previous coding was still reading.
@@ -273,6 +332,35 @@ class OnmfEngine:
             self.Wlo, self.Wlo_next = self.Wlo_next, self.Wlo
         self._cur ^= 1
         return Ht
+
+    def _step_fused(self, Xt, codes, n, w, cur):
+        """the same schedule through ONE call into libonmf_b200.so (onmf_step / onmf_step_launch + onmf_step_finish)"""
+        for t_, nm in ((Xt, "Xt"), (codes, "codes")):
+            if t_ is not None:
+                _lib._req(t_, nm, self.dtype)
+        if codes is not None and tuple(codes.shape) != (n, self.k):
+            raise _lib.OnmfKernelError("codes must be (n x k)")
+        if Xt is not None and Xt.shape[1] != self.d:
+            raise _lib.OnmfKernelError("Xt must be (n x d)")
+        if self._sb is None:
+            self._make_bufs()
+        if self.world > 1:
+            import torch.distributed as dist
+            self._plan.launch(self._sb, Xt, codes, n, cur)
+            with torch.cuda.stream(self.side):
+                dist.all_reduce(self.P[cur], group=self.pg)
+                if self.track_C:
+                    dist.all_reduce(self.P2, group=self.pg)
+            self._plan.finish(self._sb, w, cur)
+        else:
+            self._plan.step(self._sb, Xt, codes, n, w, cur)
+        self.W, self.W_next = self.W_next, self.W
+        self.G, self.G_next = self.G_next, self.G
+        if self.use_tc:
+            self.Whi, self.Whi_next = self.Whi_next, self.Whi
+            self.Wlo, self.Wlo_next = self.Wlo_next, self.Wlo
+        self._cur ^= 1
+        return self.Ht[:n] if codes is None else codes
 
     # ------------------------------------------------------------------ host-buffer entry (end-to-end path)
     def step_host(self, Xt_host: torch.Tensor, t: float, W_out_host: Optional[torch.Tensor] = None):
