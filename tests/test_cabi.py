@@ -86,3 +86,20 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["value"] > 0
     assert line["cpu_baseline"]["cores"] == 2 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def test_step_buffers_struct_layout_matches_header(tmp_path):
+    """ctypes mirror of onmf_step_buffers vs the C definition: same size and field offsets (compiled with gcc)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields = [f[0] for f in _lib.StepBuffers._fields_]
+    src = tmp_path / "layout.c"
+    body = "\n".join('  printf("%s %%zu\\n", offsetof(onmf_step_buffers, %s));' % (f, f) for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "onmf_b200.h"\nint main(void) {\n'
+                   '  printf("sizeof %zu\\n", sizeof(onmf_step_buffers));\n' + body + "\n  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert int(out["sizeof"]) == ctypes.sizeof(_lib.StepBuffers)
+    for f in fields:
+        assert int(out[f]) == getattr(_lib.StepBuffers, f).offset, f

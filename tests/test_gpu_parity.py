@@ -565,3 +565,29 @@ def test_surrogate_error_readout(golden_dir):
         got = eng.surrogate_error()
         scale = abs(np.trace(C)) + abs(ref)
         assert abs(got - ref) <= tol * scale, (got, ref)
+
+
+def test_fused_step_equals_python_composed_schedule():
+    """OnmfEngine(fused=True) (one onmf_step call per minibatch) and fused=False (the same kernels composed from Python
+    with torch events) must give bitwise identical state, in both precisions and with external codes / track_C."""
+    rng = np.random.default_rng(7)
+    d, k, n = 64, 32, 777
+    X = rng.random((n, d)); W0 = rng.random((d, k))
+    for dt_ in (torch.float32, torch.float64):
+        for kw in ({}, {"track_C": True, "use_tc": False}):
+            res = []
+            for fused in (True, False):
+                eng = OnmfEngine(d, k, alpha=0.7, dtype=dt_, device=dev(), fused=fused, **kw)
+                eng.set_state(W0)
+                Xt = tt(X, dt_)
+                H = None
+                for t in (1, 2, 3, 4):
+                    H = eng.step(Xt, float(t)).clone()
+                eng.step_with_codes(Xt, H, 5.0)                      # aggregate externally supplied codes
+                eng.step(Xt[:0], 6.0)                                # empty shard
+                W, A, B, C = eng.state()
+                torch.cuda.synchronize()
+                res.append((H, W.clone(), A.clone(), B.clone(), None if C is None else C.clone(), eng.launches))
+            for a, b in zip(res[0][:5], res[1][:5]):
+                assert (a is None and b is None) or torch.equal(a, b)
+            assert res[0][5] == res[1][5]                            # same launch accounting
