@@ -9,15 +9,17 @@
 // warp carries 32/LPC columns, a CTA carries NW warps, columns are handed out through a global ticket
 // counter.  The Gram matrix G = W^T W is staged once per CTA in shared memory when it fits (k <= 128 in
 // fp32), otherwise read through L1/L2 with the row loads of a pass batched four rows deep.  Each group
-// keeps the inverse of its active Gram block, M = G_AA^-1, packed lower-triangular in FP64 in its own
-// shared-memory tile and maintains it by bordering (atom joins) / Schur downdate (atom leaves): two
-// lane-parallel s x s passes per knot instead of sklearn's Cholesky append + two triangular solves
-// (3 s dependent steps).  M is FP64 also in the fp32 production mode: on the ill-conditioned dictionaries
-// of the first online steps (cond(G) ~ 4e5) an fp32 inverse costs 3e-3 relative code error, the fp64
-// inverse 9e-5, for ~20 % more shared-memory traffic (measured).  Covariances, correlations,
-// step lengths and coefficients are in the working precision T.  Cross-lane reductions are single REDUX
-// instructions on order-preserving integer keys (fp32) or shuffle trees (fp64 / sums); the only barriers
-// are __syncwarp().
+// keeps the INVERSE CHOLESKY FACTOR V of its active Gram block (G_AA^-1 = V V^T, V upper triangular in join
+// order) as packed FP64 columns in its own shared-memory tile.  A join appends one column after two read-only,
+// lane-parallel sweeps t = V^T g, u = V t (pivot sigma = G_jj - |t|^2); a drop closes the slot gap and
+// downdates V by Givens rotations of adjacent columns -- against sklearn's Cholesky append + two triangular
+// solves (3 s dependent steps per knot).  The equiangular weights w = G_AA^-1 1 are maintained incrementally.
+// V is FP64 also in the fp32 production mode, and is built from the FP64-accumulated Gram when the caller
+// supplies it (onmf_lasso_lars_g64): the inverse amplifies the independent per-entry rounding of an fp32 Gram
+// by cond(G) (~4e5 on the early online dictionaries), the exact Gram of the stored dictionary only sees
+// cond(W).  Covariances, correlations, step lengths and coefficients are in the working
+// precision T.  Cross-lane reductions are single REDUX instructions on order-preserving integer keys (fp32)
+// or shuffle trees (fp64 / sums); the only barriers are __syncwarp().
 //
 // Path semantics reproduced from sklearn (so the result matches the reference also where sklearn is
 // not at the exact lasso optimum):
@@ -27,13 +29,14 @@
 //     step, which is still positive inside that segment)
 //   - step gamma = min(min_pos((C-c_i)/(AA-a_i+tiny32)), C/AA); drop when a coefficient would cross 0
 //     first (gamma = z_pos), no atom joins on the iteration after a drop, the dropped atom's covariance
-//     is recomputed exactly
+//     is recomputed exactly.  fp32 only: an atom that ties EXACTLY with the joining one takes a zero-length
+//     step and joins next (sklearn steps past it; in fp32 near-ties round to exact ones, see step 6)
 //   - "alpha increasing" bail-out, degenerate-pivot rejection (cov := 0), max_iter.
 // Columns whose active set outgrows a tier's slot count are queued (device-side list) and re-walked by the next tier.
 // k <= 128: 32 -> 64 -> 128 slots, all in shared memory.  k > 128: a HYBRID first tier with 64 slots whose packed
-// inverse keeps rows 0..39 in shared memory (16 warps/SM) and rows 40..63 in an L2-resident global scratch, so the
+// factor keeps columns 0..39 in shared memory (16 warps/SM) and columns 40..63 in an L2-resident global scratch, so the
 // common case (active set <= 40) runs entirely out of shared memory and the occasional larger set costs a few global
-// accesses instead of a re-walk; then 128 slots in shared memory, then k slots with M in global memory.
+// accesses instead of a re-walk; then 128 slots in shared memory, then k slots with V in global memory.
 #include <math_constants.h>
 
 #include <type_traits>
