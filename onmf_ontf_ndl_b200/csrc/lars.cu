@@ -198,6 +198,18 @@ template <typename T> struct VecOf;
 template <> struct VecOf<float> { typedef float4 type; static constexpr int N = 4; };
 template <> struct VecOf<double> { typedef double2 type; static constexpr int N = 2; };
 
+// vector load from a global address held as an integer (keeps LDG instead of a generic LD once the base is opaque)
+__device__ __forceinline__ float4 ld_global_vec(const float4* p) {
+  float4 v;
+  asm("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_global_vec(const double2* p) {
+  double2 v;
+  asm("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
 // slot entry read by the correlation pass: (atom, normalised weight); free slots hold (0, 0)
 template <typename T> struct SlotW;
 template <> struct __align__(8) SlotW<float> { int atom; float w; };
@@ -291,6 +303,10 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
   }
   const T* Gr = GSM ? Gs : P.Gp;                       // padded rows, stride GS
   auto Gat = [&](int a, int i) -> T { return Gr[a * GS + i]; };
+  // this lane's byte offset inside a Gram row, folded into the base once: a row address is one IMAD.WIDE
+  // (kept opaque so that the compiler holds it in a register pair instead of re-deriving it from uniform registers)
+  unsigned long long Grl = reinterpret_cast<unsigned long long>(Gr) + (unsigned long long)l * sizeof(VT);
+  if (!GSM) asm volatile("" : "+l"(Grl));
   // Gram entries that enter the factor: FP64 when the caller supplies the FP64 Gram
   const double* __restrict__ G64 = P.G64;
   auto Gd = [&](int a, int i) -> double { return G64 ? G64[(size_t)a * k + i] : (double)Gat(a, i); };
@@ -596,9 +612,9 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         VT gv[UQ][NA / VEC];
 #pragma unroll
         for (int t = 0; t < UQ; ++t) {
-          const VT* row = reinterpret_cast<const VT*>(Gr + e[t].atom * GS) + l;
+          const VT* row = reinterpret_cast<const VT*>(Grl + (unsigned long long)(unsigned)e[t].atom * (unsigned)(GS * sizeof(T)));
 #pragma unroll
-          for (int v = 0; v < NA / VEC; ++v) gv[t][v] = row[v * LPC];
+          for (int v = 0; v < NA / VEC; ++v) gv[t][v] = GSM ? row[v * LPC] : ld_global_vec(row + v * LPC);
         }
 #pragma unroll
         for (int t = 0; t < UQ; ++t)
