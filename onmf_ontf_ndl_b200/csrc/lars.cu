@@ -45,6 +45,9 @@
 
 namespace onmf {
 
+#ifndef LARS_EARLY
+#define LARS_EARLY 1
+#endif
 #ifndef LARS_MAX_THREADS
 #define LARS_MAX_THREADS 512     // 16 warps/SM at <= 128 registers per thread (20 warps at 96 registers measured no faster)
 #endif
@@ -570,6 +573,21 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         __syncwarp();
       }
 
+#if LARS_EARLY
+      // The Gram rows of the first correlation batch belong to slots 0..UQ-1, whose atoms are final once the join is
+      // done: request them now, so that their L1/L2 latency overlaps the weight normalisation and the slot-table update
+      constexpr bool EARLY = (!GSM && LPC == 32);
+      VT gv0[EARLY ? UQ : 1][NA / VEC];
+      if (EARLY) {
+#pragma unroll
+        for (int t = 0; t < UQ; ++t) {
+          const int a0 = acts[t];
+          const VT* row = reinterpret_cast<const VT*>(Grl + (unsigned long long)(unsigned)(a0 >= 0 ? a0 : 0) * (unsigned)(GS * sizeof(T)));
+#pragma unroll
+          for (int v = 0; v < NA / VEC; ++v) gv0[t][v] = ld_global_vec(row + v * LPC);
+        }
+      }
+#endif
       // ---- 3. "alpha increasing" bail-out (sklearn _least_angle.py:752-765) ----
       if (!done && !skip && n_iter > 0 && a_prev < a_cur) {
         status |= 2;
@@ -604,7 +622,24 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
       T corr[NA];
 #pragma unroll
       for (int m = 0; m < NA; ++m) corr[m] = T(0);
+#if LARS_EARLY
+      if (EARLY && hwL > 0) {        // first batch: rows already requested (free slots carry weight 0, any row will do)
+        SlotW<T> e[UQ];
+#pragma unroll
+        for (int t = 0; t < UQ; ++t) e[t] = sw_[t];
+#pragma unroll
+        for (int t = 0; t < UQ; ++t)
+#pragma unroll
+          for (int v = 0; v < NA / VEC; ++v) {
+            const T* gp = reinterpret_cast<const T*>(&gv0[t][v]);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) corr[v * VEC + c] += gp[c] * e[t].w;
+          }
+      }
+      for (int q0 = EARLY ? UQ : 0; q0 < hwL; q0 += UQ) {
+#else
       for (int q0 = 0; q0 < hwL; q0 += UQ) {
+#endif
         // slots beyond this group's active count hold (atom 0, weight 0): no masking needed
         SlotW<T> e[UQ];
 #pragma unroll
