@@ -38,7 +38,7 @@ extern "C" {
 #define ONMF_E_UNSUPPORTED (-3)/* shape outside what the kernels were instantiated for    */
 #define ONMF_E_WORKSPACE (-4)  /* workspace too small                                     */
 
-/* process-wide options */
+/* options (kept per calling host thread, like the error string) */
 #define ONMF_OPT_LARS_RESERVED_SMS 1  /* SMs the persistent LARS coder leaves free (default 0) so that kernels launched
                                          on other streams (the dictionary update) run concurrently with it */
 int onmf_set_option(int key, int value);

@@ -3,7 +3,7 @@
 
 namespace onmf {
 thread_local char g_err[512] = "";
-int g_lars_reserved_sms = 0;
+thread_local int g_lars_reserved_sms = 0;   // per host thread, like the error string: engines on different threads do not interfere
 }
 
 extern "C" int onmf_version(void) { return 100; }

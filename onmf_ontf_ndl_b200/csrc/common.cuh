@@ -10,7 +10,7 @@
 namespace onmf {
 
 extern thread_local char g_err[512];
-extern int g_lars_reserved_sms;     // SMs the persistent coder leaves free for concurrently running kernels
+extern thread_local int g_lars_reserved_sms;     // SMs the persistent coder leaves free for concurrently running kernels
 
 inline int fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
