@@ -26,8 +26,8 @@ clean:
 
 .PHONY: all oracle clean variant
 
-# experimental variant of the coder: make variant NAME=pf DEFS="-DLARS_PREFETCH=1" -> scratch/variants/libonmf_b200_pf.so
+# experimental variant of the coder: make variant NAME=pf DEFS="-DLARS_PREFETCH=1" -> build/variants/libonmf_b200_pf.so
 variant: $(OBJS)
-	@mkdir -p build/$(NAME) scratch/variants
+	@mkdir -p build/$(NAME) build/variants
 	$(NVCC) $(NVFLAGS) $(DEFS) -c $(CSRC)/lars.cu -o build/$(NAME)/lars.o 2> build/$(NAME)/lars.ptxas.log || (cat build/$(NAME)/lars.ptxas.log; exit 1)
-	$(NVCC) $(ARCH) -shared -o scratch/variants/libonmf_b200_$(NAME).so $(filter-out build/lars.o,$(OBJS)) build/$(NAME)/lars.o -lcudart
+	$(NVCC) $(ARCH) -shared -o build/variants/libonmf_b200_$(NAME).so $(filter-out build/lars.o,$(OBJS)) build/$(NAME)/lars.o -lcudart

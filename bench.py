@@ -42,6 +42,12 @@ WORKLOADS = {
 }
 METRIC = "ONMF samples/sec (code+surrogate+dict update)"
 UNIT = "samples/s"
+LARS_DRAM_BYTES = 4.93e8     # ncu dram bytes of one first-tier coder launch at cfg5, N=1 (profiles/r1_lars_k256_ncu.md)
+
+
+def workload_name(name, d, k, n_global, alpha):
+    """the SAME string in both arms (the driver compares config.workload); per-arm detail goes into other config keys"""
+    return "%s: synthetic U[0,1) d=%d k=%d global minibatch %d alpha=%g" % (name, d, k, n_global, alpha)
 
 
 def measured_peaks():
@@ -186,8 +192,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: synthetic U[0,1) d=%d k=%d global minibatch %d alpha=%g" % (args.workload, d, k, n_global, alpha),
-                   "d": d, "k": k, "global_batch": n_global},
+        "config": {"workload": workload_name(args.workload, d, k, n_global, alpha), "d": d, "k": k, "global_batch": n_global,
+                   "detail": "CPU arm: %d-column sample of the minibatch per step" % cols},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": "%d of %d columns per step; numpy + scikit-learn lasso_lars (the reference's CPU path via the "
                                    "oracle port), columns split over %d worker processes with one BLAS thread each (the "
@@ -226,7 +232,7 @@ def run_ours(args):
     gw.manual_seed(0)                                                   # same W0 on every rank
     W0 = torch.rand(d, k, dtype=dt, device=dev, generator=gw)
     eng = OnmfEngine(d, k, alpha=alpha, dtype=dt, device=dev, process_group=dist.group.WORLD if world > 1 else None,
-                     collect_stats=True, fused=not args.timeline)
+                     collect_stats=True, fused=not args.timeline, lars_timing=True)
     eng.set_state(W0)
     Xb = None if eng.use_tc else torch.empty(n, d, dtype=dt, device=dev)
     main = eng.main
@@ -381,20 +387,28 @@ def run_ours(args):
     sm_clock = (clocks.get("sm_mhz") or 1900.0) * 1e6
     fp32_peak = 148 * 128 * 2 * sm_clock / 1e12               # TFLOP/s at the observed clock
     smem_peak = 148 * 128 * sm_clock / 1e9                    # GB/s  (128 B/clk/SM)
-    roofline = {"bound": "hbm", "kernel": "lars_kernel (K3 sparse coder)", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one tier-0 launch at cfg5, N=1 (ncu --set full,
-                # profiles/r1_lars_k256_ncu.md); only valid for that workload
-                "traffic": 4.94e8 if (args.workload == "cfg5" and world == 1) else None, "peak_source": peak_src,
+    fp32_ach = flop / lars_total_s / 1e12
+    smem_ach = smem_bytes / lars_total_s / 1e9
+    # The dominant kernel is the LARS coder.  Its binding roof is the FP32 FMA pipe / the L1-shared-memory data pipe
+    # ("FMA/shared-memory throughput for the lasso solver"), not HBM -- algorithmic HBM bytes per launch
+    # (read Ct, write Ht, read G once) would take 0.08 ms.  `achieved` = executed solver work counted in-kernel (per
+    # knot with active size s: one k x s correlation pass = 2ks flop, FP64 factor sweeps = 3 s^2 flop) / launch time;
+    # `peak` = 148 SMs x 128 FMA lanes x 2 at the SM clock observed during the timed region.  The HBM and
+    # shared-memory views are kept beside it.
+    roofline = {"bound": "fp32_fma", "kernel": "lars_kernel (K3 sparse coder)", "achieved": fp32_ach, "peak": fp32_peak,
+                "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
+                "peak_source": "148 SMs x 128 lanes x 2 flop x observed SM clock (%.0f MHz)" % (sm_clock / 1e6),
+                # dram__bytes_read.sum + dram__bytes_write.sum of one first-tier launch at cfg5, N=1 (ncu --set full,
+                # profiles/); only valid for that workload
+                "traffic": LARS_DRAM_BYTES if (args.workload == "cfg5" and world == 1 and not args.batch) else None,
                 "ms_per_launch": lars_ms, "share_of_step": lars_ms * K / elapsed_ms,
-                "note": "the coder is FP32-FMA / shared-memory bound, not HBM bound; see lars_work"}
-    lars_work = {"knots_per_column": stats["knots"] / cols, "mean_active": stats["sum_active"] / max(stats["knots"], 1),
-                 "max_active": stats["max_active"], "drops_per_column": stats["drops"] / cols,
-                 "overflow_columns": stats["overflow"], "flagged_columns": stats["flagged"],
-                 "executed_gflop_per_step": flop / K / 1e9, "fp32_tflops_achieved": flop / lars_total_s / 1e12,
-                 "fp32_tflops_peak_at_clock": fp32_peak, "fp32_frac": flop / lars_total_s / 1e12 / fp32_peak,
-                 "smem_gbs_achieved": smem_bytes / lars_total_s / 1e9, "smem_gbs_peak_at_clock": smem_peak,
-                 "smem_frac": smem_bytes / lars_total_s / 1e9 / smem_peak}
+                "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": achieved, "peak_gbs": hbm_peak,
+                        "frac": achieved / hbm_peak, "peak_source": peak_src},
+                "smem": {"achieved_gbs": smem_ach, "peak_gbs_at_clock": smem_peak, "frac": smem_ach / smem_peak},
+                "work": {"knots_per_column": stats["knots"] / cols, "mean_active": stats["sum_active"] / max(stats["knots"], 1),
+                         "max_active": stats["max_active"], "drops_per_column": stats["drops"] / cols,
+                         "overflow_columns": stats["overflow"], "flagged_columns": stats["flagged"],
+                         "executed_gflop_per_launch": flop / K / 1e9}}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -410,14 +424,14 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: synthetic U[0,1) d=%d k=%d global minibatch %d (%d columns/GPU) alpha=%g; "
-                               "fresh minibatch per step resampled from a resident pool; inputs (%.2f GB/GPU) larger than L2"
-                               % (args.workload, d, k, n_global, n, alpha, n * d * 4 / 1e9),
-                   "d": d, "k": k, "global_batch": n_global, "parallelism": "dp%d (column shards, all-reduce of k x (k+d))" % world},
+        "config": {"workload": workload_name(args.workload, d, k, n_global, alpha), "d": d, "k": k, "global_batch": n_global,
+                   "detail": "%d columns/GPU; fresh minibatch per step resampled from a resident pool; inputs (%.2f GB/GPU) "
+                             "larger than L2" % (n, n * d * 4 / 1e9),
+                   "parallelism": "dp%d (column shards, all-reduce of k x (k+d))" % world},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": d * k * 4,
                 "steps": e2e_steps, "api": "OnmfEngine.step_host(pinned Xt, t, W_out_host)"},
-        "roofline": roofline, "lars_work": lars_work, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

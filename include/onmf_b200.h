@@ -42,6 +42,7 @@ extern "C" {
 #define ONMF_OPT_LARS_RESERVED_SMS 1  /* SMs the persistent LARS coder leaves free (default 0) so that kernels launched
                                          on other streams (the dictionary update) run concurrently with it */
 int onmf_set_option(int key, int value);
+int onmf_get_option(int key, int* value);
 
 /* library / build identification */
 int onmf_version(void);                      /* 100*major + minor                                   */
@@ -62,7 +63,9 @@ int onmf_gather_patches(int dtype, const void* img, int H, int Wd, int C, const 
                         int64_t n, int p, void* Xt, int64_t ld, void* stream);
 
 /* column gather of a resident sample-major data pool: out[j, :] = pool[idx[j], :]
- * (X_batch = X_unfold[:, idx], src/ontf.py:231; idx as int64 like numpy's randint). */
+ * (X_batch = X_unfold[:, idx], src/ontf.py:231; idx as int64 like numpy's randint).  An index outside [0, n_pool)
+ * (numpy would raise IndexError) is never dereferenced: its output row is filled with NaN.  Likewise a patch corner
+ * outside the image in onmf_gather_patches. */
 int onmf_gather_rows(int dtype, const void* pool, int64_t n_pool, int d, const int64_t* idx,
                      int64_t n, void* Xt, void* stream);
 
@@ -188,6 +191,13 @@ int onmf_surrogate_partial_tc(const void* Ht_hi, const void* Ht_lo, const void* 
  * ------------------------------------------------------------------------------------------- */
 int onmf_update_dict(int dtype, const void* W_in, const void* A, const void* B, int d, int k,
                      void* W_out, void* stream);
+/* Dictionaries that fit one 16-CTA cluster's shared memory (d*k up to ~0.9 M fp32 / 0.45 M fp64 entries: every BASELINE
+ * config) are swept by one cluster with W resident in shared memory and need no workspace (the function returns 0).
+ * Larger ones (joint unfoldings of big tensors) fall back to a cooperative grid with W in L2 and one grid-wide barrier
+ * per atom; that path needs onmf_update_dict_workspace(dtype, d, k) bytes of scratch. */
+size_t onmf_update_dict_workspace(int dtype, int d, int k);
+int onmf_update_dict_ws(int dtype, const void* W_in, const void* A, const void* B, int d, int k,
+                        void* W_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * secondary coder: row-wise projected gradient (shipped src/onmf.py:233-271 with r=None),
@@ -220,6 +230,16 @@ int onmf_patch_grid_mean(int dtype, const void* R, int64_t ldr, int ny, int nx, 
  * MCMC states (the walk itself stays on the host). */
 int onmf_motif_patches(int dtype, const int64_t* rowptr, const int32_t* colidx, int n_nodes, const int32_t* emb,
                        int64_t n, int kk, void* Xt, void* stream);
+
+/* Batched network reconstruction: the running-mean edge weights of network_reconstruction_nx.py:475-491
+ * for a whole MCMC trajectory.  R (n x ldr) holds the patch reconstructions (R[j, q*kk + r] = (W h_j)[q*kk + r]), emb
+ * (n x kk) the node index of every motif position; every entry is added to the directed pair (emb[j,q], emb[j,r]) in an
+ * open-addressing hash table: keys (capacity x uint64, pre-filled with 0xFF bytes; key = a << 32 | b), sums (capacity
+ * doubles, zeroed), counts (capacity uint32, zeroed).  capacity: a power of two > 2 n kk^2.  Mean weight = sum / count.
+ * *failed (device uint32, zeroed) counts entries that could not be placed (negative node index, table full). */
+int onmf_edge_scatter_add(int dtype, const void* R, int64_t ldr, const int32_t* emb, int64_t n, int kk,
+                          unsigned long long* keys, double* sums, unsigned int* counts, int64_t capacity,
+                          unsigned int* failed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The fused online step: ONE host call per minibatch

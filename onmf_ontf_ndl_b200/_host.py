@@ -57,3 +57,48 @@ def to_device(M, dtype, dev):
 
 def to_numpy(T):
     return T.detach().to(torch.float64).cpu().numpy()
+
+
+def upload_indices(idx, dev):
+    """int64 index array (any shape) -> device, through pinned memory with a non-blocking copy."""
+    a = np.ascontiguousarray(idx, dtype=np.int64)
+    h = torch.from_numpy(a).pin_memory()
+    return h.to(dev, non_blocking=True)
+
+
+def broadcast_run_inputs(group, dev, d, r, W, A, B, idx_all):
+    """Multi-GPU training through the reference-facing classes: rank 0's initial state and minibatch index sequence are
+    what every rank uses (the reference draws them from numpy's global RNG, which is per process)."""
+    import torch.distributed as dist
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    flags = torch.tensor([0 if A is None else 1, 0 if idx_all is None else 1,
+                          0 if idx_all is None else idx_all.shape[0], 0 if idx_all is None else idx_all.shape[1]],
+                         dtype=torch.int64, device=dev)
+    dist.broadcast(flags, src, group=group)
+    has_ab, has_idx, s0, s1 = [int(v) for v in flags.tolist()]
+    Wd = to_device(W, torch.float64, dev)
+    dist.broadcast(Wd, src, group=group)
+    out = [Wd.cpu().numpy()]
+    for M, shape in ((A, (r, r)), (B, (r, d))):
+        if not has_ab:
+            out.append(None)
+            continue
+        Md = to_device(M, torch.float64, dev) if M is not None else torch.empty(shape, dtype=torch.float64, device=dev)
+        dist.broadcast(Md, src, group=group)
+        out.append(Md.cpu().numpy())
+    if has_idx:
+        I = torch.from_numpy(np.ascontiguousarray(idx_all, dtype=np.int64)).to(dev) if idx_all is not None and \
+            idx_all.shape == (s0, s1) else torch.empty(s0, s1, dtype=torch.int64, device=dev)
+        dist.broadcast(I, src, group=group)
+        out.append(I.cpu().numpy())
+    else:
+        out.append(None)
+    return tuple(out)
+
+
+def broadcast_indices(group, dev, idx):
+    import torch.distributed as dist
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    I = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(dev)
+    dist.broadcast(I, src, group=group)
+    return I.cpu().numpy()

@@ -43,6 +43,7 @@ SIGNATURES = {
     "onmf_gram_workspace": (_sz, [_i, _i, _i]),
     "onmf_gram_ws": (_i, [_i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "onmf_set_option": (_i, [_i, _i]),
+    "onmf_get_option": (_i, [_i, ctypes.POINTER(_i)]),
     "onmf_gram_f64_workspace": (_sz, [_i, _i]),
     "onmf_gram_f64": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "onmf_lasso_lars_g64": (_i, [_i, _vp, _vp, _i64, _i, _i, _dbl, _i, _vp, _vp, _sz, _vp, _i, _vp]),
@@ -62,12 +63,15 @@ SIGNATURES = {
     "onmf_surrogate_tc_workspace": (_sz, [_i64, _i, _i]),
     "onmf_surrogate_partial_tc": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _vp]),
     "onmf_update_dict": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "onmf_update_dict_workspace": (_sz, [_i, _i, _i]),
+    "onmf_update_dict_ws": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "onmf_pgd_sweep": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _vp, _vp]),
     "onmf_pgd_sweep_rows": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _vp, _i, _i, _vp]),
     "onmf_surrogate_error": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "onmf_pgd_code_columns": (_i, [_i, _vp, _vp, _i64, _i, _dbl, _i, _dbl, _vp, _vp]),
     "onmf_patch_grid_mean": (_i, [_i, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "onmf_motif_patches": (_i, [_i, _vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "onmf_edge_scatter_add": (_i, [_i, _vp, _i64, _vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _vp]),
     "onmf_step_plan_create": (_i, [ctypes.POINTER(_vp), _i]),
     "onmf_step_plan_destroy": (_i, [_vp]),
     "onmf_step_plan_mark_state": (_i, [_vp, _vp]),
@@ -174,10 +178,17 @@ def transpose(src, out, stream=None):
 
 
 OPT_LARS_RESERVED_SMS = 1
+MAX_COMPONENTS = 512          # largest n_components the LARS coder is instantiated for (csrc/lars.cu k_class)
 
 
 def set_option(key, value):
     _check(load().onmf_set_option(int(key), int(value)), "onmf_set_option")
+
+
+def get_option(key):
+    v = _i(0)
+    _check(load().onmf_get_option(int(key), ctypes.byref(v)), "onmf_get_option")
+    return int(v.value)
 
 
 def gram_workspace(dtype, d, k):
@@ -271,10 +282,19 @@ def axpby(a, x, b, y, stream=None):
     _check(load().onmf_axpby(dt(x), x.numel(), float(a), _ptr(x), float(b), _ptr(y), _stream(stream)), "onmf_axpby")
 
 
-def update_dict(W, A, B, W_out, stream=None):
+def update_dict_workspace(dtype, d, k):
+    return int(load().onmf_update_dict_workspace(F64 if dtype == torch.float64 else F32, d, k))
+
+
+def update_dict(W, A, B, W_out, stream=None, workspace=None):
     _req(W, "W"); _req(A, "A", W.dtype); _req(B, "B", W.dtype); _req(W_out, "W_out", W.dtype)
     d, k = W.shape
-    _check(load().onmf_update_dict(dt(W), _ptr(W), _ptr(A), _ptr(B), d, k, _ptr(W_out), _stream(stream)), "onmf_update_dict")
+    if workspace is None:
+        nb = update_dict_workspace(W.dtype, d, k)
+        if nb:          # large dictionaries only: the cooperative-grid fallback exchanges column norms through this scratch
+            workspace = torch.empty(nb, dtype=torch.uint8, device=W.device)
+    _check(load().onmf_update_dict_ws(dt(W), _ptr(W), _ptr(A), _ptr(B), d, k, _ptr(W_out), _ptr(workspace),
+                                      workspace.numel() if workspace is not None else 0, _stream(stream)), "onmf_update_dict")
     return W_out
 
 
@@ -373,6 +393,15 @@ def motif_patches(rowptr, colidx, emb, out, stream=None):
     _check(load().onmf_motif_patches(dt(out), _ptr(rowptr), _ptr(colidx), rowptr.shape[0] - 1, _ptr(emb), n, kk, _ptr(out),
                                      _stream(stream)), "onmf_motif_patches")
     return out
+
+
+def edge_scatter_add(R, emb, keys, sums, counts, failed, stream=None):
+    _req(R, "R"); _req(emb, "emb", torch.int32); _req(keys, "keys", torch.int64); _req(sums, "sums", torch.float64)
+    _req(counts, "counts", torch.int32); _req(failed, "failed", torch.int32)
+    n, kk = emb.shape
+    _check(load().onmf_edge_scatter_add(dt(R), _ptr(R), R.stride(0) if n else kk * kk, _ptr(emb), n, kk, _ptr(keys),
+                                        _ptr(sums), _ptr(counts), keys.numel(), _ptr(failed), _stream(stream)),
+           "onmf_edge_scatter_add")
 
 
 # ---- fused step (csrc/step.cu) ---------------------------------------------------------------------

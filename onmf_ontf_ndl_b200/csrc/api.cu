@@ -19,3 +19,13 @@ extern "C" int onmf_set_option(int key, int value) {
   }
   return onmf::fail(ONMF_E_ARG, "set_option: unknown key");
 }
+
+extern "C" int onmf_get_option(int key, int* value) {
+  if (!value) return onmf::fail(ONMF_E_ARG, "get_option: null pointer");
+  switch (key) {
+    case ONMF_OPT_LARS_RESERVED_SMS:
+      *value = onmf::g_lars_reserved_sms;
+      return ONMF_OK;
+  }
+  return onmf::fail(ONMF_E_ARG, "get_option: unknown key");
+}

@@ -122,8 +122,103 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
   }
 }
 
+// Fallback for dictionaries that do not fit one cluster's shared memory (d*k beyond ~0.9 M fp32 / 0.45 M fp64 entries, e.g.
+// joint unfoldings of large tensors): a cooperative grid keeps W in global memory (L2 resident), every CTA owns a row
+// slab -- rows are only ever read and written by their owner, the sweep is row-separable -- and the column norm is a
+// fixed-order sum of per-CTA partials exchanged through global memory with ONE grid.sync() per atom.
 template <typename T>
-static int update_dict_t(const T* Win, const T* A, const T* B, int d, int k, T* Wout, cudaStream_t st) {
+__global__ void __launch_bounds__(256) bcd_global_kernel(const T* __restrict__ Win, const T* __restrict__ A, const T* __restrict__ B,
+                                                         T* __restrict__ Wout, int d, int k, int rpb, T* __restrict__ partials) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* aj = reinterpret_cast<T*>(smem_raw);              // k     column j of A
+  T* wn = aj + k;                                      // rpb   the slab's new (unnormalised) column j
+  T* warp_part = wn + rpb;                             // 8
+  __shared__ T tot_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int nb = gridDim.x;
+  const int row0 = blockIdx.x * rpb;
+  const int nrows = max(0, min(rpb, d - row0));
+  if (Win != Wout)
+    for (long long idx = tid; idx < (long long)nrows * k; idx += blockDim.x) Wout[(size_t)row0 * k + idx] = Win[(size_t)row0 * k + idx];
+  __syncthreads();
+  for (int j = 0; j < k; ++j) {
+    const int par = j & 1;
+    for (int q = tid; q < k; q += blockDim.x) aj[q] = A[(size_t)q * k + j];
+    __syncthreads();
+    const T c = T(1) / (aj[j] + T(1));
+    T sq = T(0);
+    for (int r = warp; r < nrows; r += nwarp) {        // one warp per row, rows of a warp in increasing order
+      const T* wrow = Wout + (size_t)(row0 + r) * k;
+      T dot = T(0);
+      for (int q = lane; q < k; q += 32) dot += wrow[q] * aj[q];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+      T v = wrow[j] - c * (dot - B[(size_t)j * d + row0 + r]);
+      v = v > T(0) ? v : T(0);
+      if (lane == 0) { wn[r] = v; sq += v * v; }
+    }
+    if (lane == 0) warp_part[warp] = sq;
+    __syncthreads();
+    if (tid == 0) {
+      T v = T(0);
+      for (int w = 0; w < nwarp; ++w) v += warp_part[w];
+      partials[(size_t)par * nb + blockIdx.x] = v;
+    }
+    grid.sync();
+    if (warp == 0) {                                   // fixed-order total: lane-strided partial sums, then a shuffle tree
+      T v = T(0);
+      for (int b = lane; b < nb; b += 32) v += partials[(size_t)par * nb + b];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) tot_s = v;
+    }
+    __syncthreads();
+    const T nrm = sqrt(tot_s);
+    const T sc = T(1) / (nrm > T(1) ? nrm : T(1));
+    for (int r = tid; r < nrows; r += blockDim.x) Wout[(size_t)(row0 + r) * k + j] = sc * wn[r];
+    __syncthreads();
+  }
+}
+
+template <typename T>
+static int update_dict_global_t(const T* Win, const T* A, const T* B, int d, int k, T* Wout, void* ws, size_t ws_bytes,
+                                cudaStream_t st) {
+  int dev = 0, coop = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop) return fail(ONMF_E_UNSUPPORTED, "update_dict: dictionary too large for one cluster and no cooperative launch");
+  int nb = num_sms();
+  if (nb > d) nb = d;
+  int rpb = cdiv(d, nb);
+  nb = cdiv(d, rpb);
+  const size_t smem = ((size_t)k + rpb + 8) * sizeof(T);
+  if (smem > (size_t)max_smem_optin()) return fail(ONMF_E_UNSUPPORTED, "update_dict: dictionary too large (row slab exceeds shared memory)");
+  if (!ws || ws_bytes < 2 * (size_t)num_sms() * sizeof(double))
+    return fail(ONMF_E_WORKSPACE, "update_dict: this dictionary needs onmf_update_dict_ws with a workspace of onmf_update_dict_workspace bytes");
+  auto kern = bcd_global_kernel<T>;
+  ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  T* partials = (T*)ws;
+  void* args[] = {(void*)&Win, (void*)&A, (void*)&B, (void*)&Wout, (void*)&d, (void*)&k, (void*)&rpb, (void*)&partials};
+  ONMF_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(nb), dim3(256), args, smem, st));
+  return ONMF_OK;
+}
+
+template <typename T>
+static bool cluster_fits(int d, int k) {
+  const size_t smem_cap = (size_t)max_smem_optin() - 1024;
+  const int rpc = cdiv(d, BCD_MAX_CLUSTER);
+  if (rpc > 1024) return false;
+  int tpr = 32;
+  while (tpr > 1 && rpc * tpr > 1024) tpr >>= 1;
+  while (tpr > 1 && tpr * 2 > k) tpr >>= 1;
+  const int ks = round_up(k, 32) + (tpr < 32 ? tpr : 1);
+  return ((size_t)rpc * ks + 2 * (size_t)k + 32 + 2 * BCD_MAX_CLUSTER) * sizeof(T) <= smem_cap;
+}
+
+template <typename T>
+static int update_dict_t(const T* Win, const T* A, const T* B, int d, int k, T* Wout, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!cluster_fits<T>(d, k)) return update_dict_global_t<T>(Win, A, B, d, k, Wout, ws, ws_bytes, st);
   const size_t smem_cap = (size_t)max_smem_optin() - 1024;
   // smallest power-of-two cluster whose slabs fit; prefer <= 128 rows per CTA so several lanes share a row
   int cs = 1;
@@ -164,12 +259,26 @@ static int update_dict_t(const T* Win, const T* A, const T* B, int d, int k, T* 
 
 }  // namespace onmf
 
-extern "C" int onmf_update_dict(int dtype, const void* W_in, const void* A, const void* B, int d, int k, void* W_out,
-                                void* stream) {
+extern "C" size_t onmf_update_dict_workspace(int dtype, int d, int k) {
+  using namespace onmf;
+  if (d <= 0 || k <= 0) return 0;
+  const bool fits = dtype == ONMF_F64 ? cluster_fits<double>(d, k) : cluster_fits<float>(d, k);
+  return fits ? 0 : 2 * (size_t)num_sms() * sizeof(double);
+}
+
+extern "C" int onmf_update_dict_ws(int dtype, const void* W_in, const void* A, const void* B, int d, int k, void* W_out,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
   using namespace onmf;
   if (!W_in || !A || !B || !W_out || d <= 0 || k <= 0) return fail(ONMF_E_ARG, "update_dict: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == ONMF_F32) return update_dict_t<float>((const float*)W_in, (const float*)A, (const float*)B, d, k, (float*)W_out, st);
-  if (dtype == ONMF_F64) return update_dict_t<double>((const double*)W_in, (const double*)A, (const double*)B, d, k, (double*)W_out, st);
+  if (dtype == ONMF_F32)
+    return update_dict_t<float>((const float*)W_in, (const float*)A, (const float*)B, d, k, (float*)W_out, workspace, workspace_bytes, st);
+  if (dtype == ONMF_F64)
+    return update_dict_t<double>((const double*)W_in, (const double*)A, (const double*)B, d, k, (double*)W_out, workspace, workspace_bytes, st);
   return fail(ONMF_E_ARG, "update_dict: bad dtype");
+}
+
+extern "C" int onmf_update_dict(int dtype, const void* W_in, const void* A, const void* B, int d, int k, void* W_out,
+                                void* stream) {
+  return onmf_update_dict_ws(dtype, W_in, A, B, d, k, W_out, nullptr, 0, stream);
 }

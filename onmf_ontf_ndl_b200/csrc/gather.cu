@@ -10,6 +10,10 @@
 
 namespace onmf {
 
+template <typename T> __device__ __forceinline__ T nan_of();
+template <> __device__ __forceinline__ float nan_of<float>() { return __int_as_float(0x7fc00000); }
+template <> __device__ __forceinline__ double nan_of<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+
 template <typename T>
 __global__ void gather_patches_kernel(const T* __restrict__ img, int H, int Wd, int C, const int32_t* __restrict__ coords,
                                       long long n, int p, T* __restrict__ Xt, long long ld) {
@@ -22,21 +26,30 @@ __global__ void gather_patches_kernel(const T* __restrict__ img, int H, int Wd, 
     const long long j = t / p;
     const int r = (int)(t - j * p);
     const int a = coords[2 * j], b = coords[2 * j + 1];
-    const T* src = img + ((size_t)(a + r) * Wd + b) * C;
     T* dst = Xt + (size_t)j * ld + (size_t)r * run;
+    if (a < 0 || b < 0 || a > H - p || b > Wd - p) {        // corner outside the image: never read out of bounds,
+      for (int e = lane; e < run; e += 32) dst[e] = nan_of<T>();   // poison the patch so the error is loud downstream
+      continue;
+    }
+    const T* src = img + ((size_t)(a + r) * Wd + b) * C;
     for (int e = lane; e < run; e += 32) dst[e] = src[e];
   }
 }
 
 template <typename T>
-__global__ void gather_rows_kernel(const T* __restrict__ pool, int d, const long long* __restrict__ idx, long long n,
-                                   T* __restrict__ Xt) {
+__global__ void gather_rows_kernel(const T* __restrict__ pool, long long n_pool, int d, const long long* __restrict__ idx,
+                                   long long n, T* __restrict__ Xt) {
   const int lane = threadIdx.x & 31;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long j = wid; j < n; j += nw) {
-    const T* src = pool + (size_t)idx[j] * d;
+    const long long i = idx[j];
     T* dst = Xt + (size_t)j * d;
+    if (i < 0 || i >= n_pool) {                               // bad index: NaN row instead of an out-of-bounds read
+      for (int e = lane; e < d; e += 32) dst[e] = nan_of<T>();
+      continue;
+    }
+    const T* src = pool + (size_t)i * d;
     for (int e = lane; e < d; e += 32) dst[e] = src[e];
   }
 }
@@ -62,11 +75,15 @@ __global__ void transpose_kernel(const TI* __restrict__ src, long long rows, lon
 // independently per sample.  One warp per sample; h lives in registers (atom i on lane i%32).
 template <typename T, int NA>
 __global__ void pgd_sweep_kernel(const T* __restrict__ G, const T* __restrict__ Ct, long long n, int k, T alpha, T scale,
-                                 T* __restrict__ Ht, int q_begin, int q_end) {
+                                 T* __restrict__ Ht, int q_begin, int q_end, int gsm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* Gs = reinterpret_cast<T*>(smem_raw);
-  for (int i = threadIdx.x; i < k * k; i += blockDim.x) Gs[i] = G[i];
-  __syncthreads();
+  const T* Gs = G;                 // Gram matrices beyond the shared-memory capacity are read through L1/L2
+  if (gsm) {
+    T* Gw = reinterpret_cast<T*>(smem_raw);
+    for (int i = threadIdx.x; i < k * k; i += blockDim.x) Gw[i] = G[i];
+    __syncthreads();
+    Gs = Gw;
+  }
   const int lane = threadIdx.x & 31;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -109,11 +126,15 @@ __global__ void pgd_sweep_kernel(const T* __restrict__ G, const T* __restrict__ 
 // the spectral norm of src/onmf.py:265 is the vector 2-norm).  One warp per sample; Ht holds H0 on entry.
 template <typename T, int NA>
 __global__ void pgd_columns_kernel(const T* __restrict__ G, const T* __restrict__ Ct, long long n, int k, T alpha, int sub_iter,
-                                   T stopping_diff, T* __restrict__ Ht) {
+                                   T stopping_diff, T* __restrict__ Ht, int gsm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* Gs = reinterpret_cast<T*>(smem_raw);
-  for (int i = threadIdx.x; i < k * k; i += blockDim.x) Gs[i] = G[i];
-  __syncthreads();
+  const T* Gs = G;                 // Gram matrices beyond the shared-memory capacity are read through L1/L2
+  if (gsm) {
+    T* Gw = reinterpret_cast<T*>(smem_raw);
+    for (int i = threadIdx.x; i < k * k; i += blockDim.x) Gw[i] = G[i];
+    __syncthreads();
+    Gs = Gw;
+  }
   const int lane = threadIdx.x & 31;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -218,7 +239,8 @@ template <typename T>
 static int pgd_t(const T* G, const T* Ct, long long n, int k, double alpha, int it, T* Ht, int q_begin, int q_end,
                  cudaStream_t st) {
   size_t smem = (size_t)k * k * sizeof(T);
-  if (smem > (size_t)max_smem_optin()) return fail(ONMF_E_UNSUPPORTED, "pgd_sweep: Gram does not fit in shared memory");
+  const int gsm = smem <= (size_t)max_smem_optin() ? 1 : 0;
+  if (!gsm) smem = 0;
   const T scale = (T)sqrt((double)it + 10.0);
   int threads = 256;
   long long warps = n;
@@ -229,7 +251,7 @@ static int pgd_t(const T* G, const T* Ct, long long n, int k, double alpha, int 
   {                                                                                                  \
     auto kern = pgd_sweep_kernel<T, NA>;                                                             \
     ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    kern<<<grid, threads, smem, st>>>(G, Ct, n, k, (T)alpha, scale, Ht, q_begin, q_end);             \
+    kern<<<grid, threads, smem, st>>>(G, Ct, n, k, (T)alpha, scale, Ht, q_begin, q_end, gsm);             \
   }
   if (k <= 32) ONMF_PGD(1)
   else if (k <= 64) ONMF_PGD(2)
@@ -281,8 +303,8 @@ extern "C" int onmf_gather_rows(int dtype, const void* pool, int64_t n_pool, int
   int threads = 256;
   int grid = (int)cdiv<long long>(n * 32, threads);
   if (grid > 8 * num_sms()) grid = 8 * num_sms();
-  if (dtype == ONMF_F32) gather_rows_kernel<float><<<grid, threads, 0, st>>>((const float*)pool, d, (const long long*)idx, n, (float*)Xt);
-  else if (dtype == ONMF_F64) gather_rows_kernel<double><<<grid, threads, 0, st>>>((const double*)pool, d, (const long long*)idx, n, (double*)Xt);
+  if (dtype == ONMF_F32) gather_rows_kernel<float><<<grid, threads, 0, st>>>((const float*)pool, n_pool, d, (const long long*)idx, n, (float*)Xt);
+  else if (dtype == ONMF_F64) gather_rows_kernel<double><<<grid, threads, 0, st>>>((const double*)pool, n_pool, d, (const long long*)idx, n, (double*)Xt);
   else return fail(ONMF_E_ARG, "gather_rows: bad dtype");
   ONMF_LAUNCH_CHECK("gather_rows_kernel");
   return ONMF_OK;
@@ -328,7 +350,8 @@ extern "C" int onmf_pgd_code_columns(int dtype, const void* G, const void* Ct, i
   cudaStream_t st = (cudaStream_t)stream;
   size_t tsz = dtype == ONMF_F64 ? 8 : 4;
   size_t smem = (size_t)k * k * tsz;
-  if (smem > (size_t)max_smem_optin()) return fail(ONMF_E_UNSUPPORTED, "pgd_code_columns: Gram does not fit in shared memory");
+  const int gsm = smem <= (size_t)max_smem_optin() ? 1 : 0;
+  if (!gsm) smem = 0;
   int threads = 256;
   int grid = (int)cdiv<long long>(n * 32, threads);
   if (grid > 4 * num_sms()) grid = 4 * num_sms();
@@ -336,7 +359,7 @@ extern "C" int onmf_pgd_code_columns(int dtype, const void* G, const void* Ct, i
   {                                                                                                    \
     auto kern = pgd_columns_kernel<TT, NA>;                                                            \
     ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    kern<<<grid, threads, smem, st>>>((const TT*)G, (const TT*)Ct, n, k, (TT)alpha, sub_iter, (TT)stopping_diff, (TT*)Ht); \
+    kern<<<grid, threads, smem, st>>>((const TT*)G, (const TT*)Ct, n, k, (TT)alpha, sub_iter, (TT)stopping_diff, (TT*)Ht, gsm); \
   }
 #define ONMF_PGDC_K(TT)                                   \
   if (k <= 32) ONMF_PGDC(TT, 1)                           \
@@ -411,5 +434,68 @@ extern "C" int onmf_motif_patches(int dtype, const int64_t* rowptr, const int32_
   else if (dtype == ONMF_F64) motif_patches_kernel<double><<<grid, 256, 0, st>>>((const long long*)rowptr, colidx, n_nodes, emb, n, kk, (double*)Xt);
   else return fail(ONMF_E_ARG, "motif_patches: bad dtype");
   ONMF_LAUNCH_CHECK("motif_patches_kernel");
+  return ONMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched network reconstruction (second half): running-mean edge weights of
+// network_reconstruction_nx.py:475-491.  The reference codes ONE k x k patch per MCMC step and, for every (q, r), folds
+// patch_recons[q, r] into the weight of the directed edge (emb[q], emb[r]) as a running mean ((j*w + x)/(j + 1), count
+// j + 1 kept in a second DiGraph).  A running mean over a sequence is its arithmetic mean, so for a whole trajectory the
+// result is sum / count per distinct (a, b): one thread per (state, q, r) entry adds into an open-addressing hash table
+// keyed by (a << 32 | b) -- FP64 sums, integer counts.  The caller sizes the table (power of two, > 2x the entries is
+// always enough), fills the keys with 0xFF bytes and zeroes sums / counts.
+// ------------------------------------------------------------------------------------------------
+namespace onmf {
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {    // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+
+template <typename T>
+__global__ void edge_scatter_kernel(const T* __restrict__ R, long long ldr, const int* __restrict__ emb, long long n, int kk,
+                                    unsigned long long* __restrict__ keys, double* __restrict__ sums,
+                                    unsigned int* __restrict__ cnts, unsigned long long mask, unsigned int* __restrict__ failed) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (long long)kk * kk;
+  if (idx >= n * per) return;
+  const long long j = idx / per;
+  const int e = (int)(idx - j * per);
+  const int q = e / kk, r = e - q * kk;
+  const int a = emb[j * kk + q], b = emb[j * kk + r];
+  if (a < 0 || b < 0) { atomicAdd(failed, 1u); return; }
+  const unsigned long long key = ((unsigned long long)(unsigned)a << 32) | (unsigned long long)(unsigned)b;
+  const double val = (double)R[(size_t)j * ldr + e];
+  unsigned long long h = mix64(key) & mask;
+  for (unsigned long long probe = 0; probe <= mask; ++probe) {
+    const unsigned long long prev = atomicCAS(&keys[h], ~0ULL, key);
+    if (prev == ~0ULL || prev == key) {
+      atomicAdd(&sums[h], val);
+      atomicAdd(&cnts[h], 1u);
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+  atomicAdd(failed, 1u);                      // table full (caller sized it too small)
+}
+}  // namespace onmf
+
+extern "C" int onmf_edge_scatter_add(int dtype, const void* R, int64_t ldr, const int32_t* emb, int64_t n, int kk,
+                                     unsigned long long* keys, double* sums, unsigned int* counts, int64_t capacity,
+                                     unsigned int* failed, void* stream) {
+  if (!R || !emb || !keys || !sums || !counts || !failed || n < 0 || kk <= 0 || ldr < (int64_t)kk * kk)
+    return fail(ONMF_E_ARG, "edge_scatter_add: bad argument");
+  if (capacity <= 0 || (capacity & (capacity - 1))) return fail(ONMF_E_ARG, "edge_scatter_add: capacity must be a power of two");
+  if (n == 0) return ONMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long tot = n * (long long)kk * kk;
+  const unsigned grid = (unsigned)cdiv<long long>(tot, 256);
+  const unsigned long long mask = (unsigned long long)capacity - 1;
+  if (dtype == ONMF_F32) edge_scatter_kernel<float><<<grid, 256, 0, st>>>((const float*)R, ldr, emb, n, kk, keys, sums, counts, mask, failed);
+  else if (dtype == ONMF_F64) edge_scatter_kernel<double><<<grid, 256, 0, st>>>((const double*)R, ldr, emb, n, kk, keys, sums, counts, mask, failed);
+  else return fail(ONMF_E_ARG, "edge_scatter_add: bad dtype");
+  ONMF_LAUNCH_CHECK("edge_scatter_kernel");
   return ONMF_OK;
 }

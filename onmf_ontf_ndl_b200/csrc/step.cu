@@ -115,7 +115,8 @@ extern "C" int onmf_step_launch(onmf_step_plan* p, const onmf_step_buffers* b, c
 
   // ---- side: dictionary update with the OLD aggregates, then everything the coder derives from the dictionary ----
   ONMF_CUDA(cudaStreamWaitEvent(side, p->ev_code, 0));
-  if ((rc = onmf_update_dict(dt, b->W[cur], b->A, b->B, d, k, b->W[nx], side))) return rc;
+  // (the large-dictionary fallback of the update borrows the Gram workspace: same stream, used one after the other)
+  if ((rc = onmf_update_dict_ws(dt, b->W[cur], b->A, b->B, d, k, b->W[nx], b->ws_gram, b->ws_gram_bytes, side))) return rc;
   if ((rc = onmf_gram_f64(dt, b->W[nx], d, k, b->G[nx], nullptr, b->ws_gram, b->ws_gram_bytes, side))) return rc;
   p->launches += 3;
   if (b->use_tc) {

@@ -29,11 +29,17 @@ class OnmfEngine:
     def __init__(self, d: int, k: int, alpha: float = 1.0, beta: Optional[float] = None,
                  dtype: torch.dtype = torch.float32, device=None, max_iter: int = 1000,
                  process_group=None, track_C: bool = False, collect_stats: bool = False, use_tc=None,
-                 reserve_sms: Optional[int] = None, fused: bool = True):
+                 reserve_sms: Optional[int] = None, fused: bool = True, lars_timing: bool = False):
         if not torch.cuda.is_available():
             raise _lib.OnmfKernelError("OnmfEngine needs a CUDA device (there is no CPU path)")
         _lib.load()
         self.d, self.k = int(d), int(k)
+        if self.d <= 0 or self.k <= 0:
+            raise _lib.OnmfKernelError("OnmfEngine: d and k must be positive")
+        if self.k > _lib.MAX_COMPONENTS:
+            # fail before any training starts (the coder's atom classes stop at 512; see INTEGRATION.md "Limits")
+            raise _lib.OnmfKernelError("OnmfEngine: n_components = %d > %d is not instantiated in the LARS coder"
+                                       % (self.k, _lib.MAX_COMPONENTS))
         self.alpha = float(alpha)
         self.beta = 1.0 if beta is None else float(beta)
         self.dtype = dtype
@@ -74,7 +80,8 @@ class OnmfEngine:
         self._collect = bool(collect_stats)
         self.main = torch.cuda.current_stream(dev)
         self.side = torch.cuda.Stream(dev, priority=-1)     # dictionary update / all-reduce: short kernels, scheduled first
-        self._ws_gram = torch.empty(_lib.gram_f64_workspace(d, k), dtype=torch.uint8, device=dev)
+        self._ws_gram = torch.empty(max(_lib.gram_f64_workspace(d, k), _lib.update_dict_workspace(dt_, d, k)),
+                                    dtype=torch.uint8, device=dev)
         self._ws_gram_s = torch.empty(_lib.gram_f64_workspace(d, k), dtype=torch.uint8, device=dev)  # sparse_code(foreign W)
         if reserve_sms is None and os.environ.get("ONMF_RESERVE_SMS"):
             reserve_sms = int(os.environ["ONMF_RESERVE_SMS"])
@@ -88,7 +95,8 @@ class OnmfEngine:
         # fused step (csrc/step.cu): one C call per minibatch enqueues the whole schedule; the Python-composed schedule
         # below (same kernels, same ordering, torch events) remains for analysis (bench.py --timeline)
         self.fused = bool(fused)
-        self._plan = _lib.StepPlan(timing_slots=256) if self.fused else None
+        # the coder-launch timing ring (two timed events per step) is only created when somebody reads it (bench.py)
+        self._plan = _lib.StepPlan(timing_slots=256 if lars_timing else 0) if self.fused else None
         self._pairs = None
         self._sb = None
 
@@ -152,6 +160,20 @@ class OnmfEngine:
                 dst.copy_(torch.as_tensor(src).to(self.device, self.dtype))
         self._derive(self.W, self.G, getattr(self, "Whi", None), getattr(self, "Wlo", None), self.main)
         # the first dictionary update (side stream) reads W, A, B and shares the Gram workspace with the derive above
+        if self._plan is not None:
+            self._plan.mark_state(self.main)
+        else:
+            self._ev_code.record(self.main)
+
+    def reset_aggregates(self, A=None, B=None, C=None):
+        """Overwrite the aggregates (device tensors or arrays; None = keep) between steps.  The copies run on the main
+        stream AFTER everything the side stream still has in flight (the previous step's blend), and the next dictionary
+        update -- which reads A, B on the side stream -- is ordered behind them (the plan's state event is re-recorded)."""
+        self.flush()
+        for dst, src in ((self.A, A), (self.B, B), (self.C, C)):
+            if dst is None or src is None:
+                continue
+            dst.copy_(torch.as_tensor(src).to(self.device, self.dtype))
         if self._plan is not None:
             self._plan.mark_state(self.main)
         else:
@@ -252,7 +274,7 @@ class OnmfEngine:
         # buffer the previous coding was still reading.
         with torch.cuda.stream(side):
             side.wait_event(self._ev_code)
-            _lib.update_dict(self.W, self.A, self.B, self.W_next, stream=side)
+            _lib.update_dict(self.W, self.A, self.B, self.W_next, stream=side, workspace=self._ws_gram)
             self._derive(self.W_next, self.G_next, getattr(self, "Whi_next", None), getattr(self, "Wlo_next", None), side)
             self._ev_W.record(side)
             self.launches += 1
@@ -283,10 +305,13 @@ class OnmfEngine:
                     # landed: both become runnable together and the high-priority side stream is placed first.
                     main.wait_event(self._ev_AB)
                 rsv = self.reserve_sms if self.reserve_sms is not None else (8 if n * self.k <= 131072 * 256 else 0)
+                saved = _lib.get_option(_lib.OPT_LARS_RESERVED_SMS)
                 _lib.set_option(_lib.OPT_LARS_RESERVED_SMS, rsv)
-                _lib.lasso_lars(self.G, Ct, self.d, self.alpha, Ht, self._ws_lars, max_iter=self.max_iter,
-                                stats=self._stats_ptr(), stream=main)
-                _lib.set_option(_lib.OPT_LARS_RESERVED_SMS, 0)
+                try:
+                    _lib.lasso_lars(self.G, Ct, self.d, self.alpha, Ht, self._ws_lars, max_iter=self.max_iter,
+                                    stats=self._stats_ptr(), stream=main)
+                finally:
+                    _lib.set_option(_lib.OPT_LARS_RESERVED_SMS, saved)
                 self.launches += 1 + self._lars_launches()
             if self.use_tc:
                 _lib.split_tf32(Ht, self.Hhi[:n], self.Hlo[:n], stream=main)

@@ -21,10 +21,14 @@ Default semantics are the `ontf.py` / paper recursion (aggregates accumulate acr
 is the positive lasso -- BASELINE.json north_star: "a batched nonnegative-lasso kernel replaces
 sparse_code").  `compat="shipped_onmf"` reproduces the literal shipped file instead: random-H0
 projected-gradient coder (src/onmf.py:87, :233-271) and the aggregate re-binding of src/onmf.py:217.
-alpha=None means 0 here (src/onmf.py:82-84).
+
+alpha=None follows the coder, as in the reference: every lasso_lars call site there uses transform_alpha=2 for None
+(src/ontf.py:79-81 and the lasso variant kept as a string literal in src/onmf.py:71-80), the projected-gradient coder
+uses 0 (src/onmf.py:82-84).  All shipped drivers pass alpha=None.
 
 Extra keywords (not in the reference): precision ("fp32" | "fp64"), coder ("lasso_lars" | "pgd"),
-compat (None | "shipped_onmf"), track_C (maintain the d x d aggregate C even without full_code).
+compat (None | "shipped_onmf"), track_C (maintain the d x d aggregate C even without full_code),
+process_group (data-parallel training over several GPUs, see Online_NTF; lasso_lars coder, subsample=True or False).
 """
 from __future__ import annotations
 
@@ -33,6 +37,7 @@ import torch
 
 from . import _host, _lib
 from .engine import OnmfEngine
+from .parallel import default_group, shard_range
 
 DEBUG = False
 
@@ -56,7 +61,8 @@ class Online_NMF():
                  precision=None,
                  coder=None,
                  compat=None,
-                 track_C=None):
+                 track_C=None,
+                 process_group=None):
         self.X = X
         self.n_components = n_components
         self.batch_size = batch_size
@@ -84,9 +90,24 @@ class Online_NMF():
         self._dtype = _host.torch_dtype(precision)
         self.track_C = track_C
         self.lars_stats = None
+        self.process_group = process_group
+        self._engines = {}
 
     def _alpha(self):
-        return 0 if self.alpha is None else self.alpha        # src/onmf.py:82-84
+        if self.alpha is None:
+            return 2 if self.coder == "lasso_lars" else 0     # src/ontf.py:79-81 (lasso) / src/onmf.py:82-84 (PGD)
+        return self.alpha
+
+    def _engine(self, d, r, track_C=False, group=None):
+        """one engine per (d, r, track_C, group) kept on the object (drivers call sparse_code / step per patch or epoch)"""
+        key = (int(d), int(r), bool(track_C), id(group) if group is not None else None)
+        eng = self._engines.get(key)
+        if eng is None or eng.alpha != float(self._alpha()) or eng.beta != (1.0 if self.beta is None else float(self.beta)):
+            eng = OnmfEngine(d, r, alpha=self._alpha(), beta=self.beta, dtype=self._dtype, device=_host.device(),
+                             track_C=track_C, collect_stats=True, process_group=group)
+            self._engines[key] = eng
+        eng.stats.zero_()
+        return eng
 
     # -- coders ----------------------------------------------------------------------------------
     def _code_device(self, eng, Xt, Wd):
@@ -103,8 +124,7 @@ class Online_NMF():
         dev = _host.device()
         Xt = _host.to_sample_major(X, self._dtype, dev)
         Wd = _host.to_device(W, self._dtype, dev)
-        eng = OnmfEngine(Wd.shape[0], Wd.shape[1], alpha=self._alpha(), beta=self.beta, dtype=self._dtype,
-                         device=dev, collect_stats=True)
+        eng = self._engine(Wd.shape[0], Wd.shape[1])
         Ht = self._code_device(eng, Xt, Wd)
         self.lars_stats = eng.read_stats()
         return _host.from_sample_major(Ht)
@@ -121,7 +141,7 @@ class Online_NMF():
         dev = _host.device()
         d, r = np.shape(W)
         has_C = len(aggregates) == 3
-        eng = OnmfEngine(d, r, alpha=self._alpha(), beta=self.beta, dtype=self._dtype, device=dev, track_C=has_C)
+        eng = self._engine(d, r, track_C=has_C)
         eng.set_state(W, aggregates[0], aggregates[1], aggregates[2] if has_C else None)
         Xt = _host.to_sample_major(X, self._dtype, dev)
         H1 = self._step_device(eng, Xt, float(t))
@@ -160,32 +180,48 @@ class Online_NMF():
         t0 = self.history
 
         pool = _host.to_sample_major(X, self._dtype, dev)        # (n x d)
-        eng = OnmfEngine(d, r, alpha=self._alpha(), beta=self.beta, dtype=self._dtype, device=dev,
-                         track_C=want_C, collect_stats=True)
+        group, world, rank = default_group(self.process_group)
+        if world > 1:
+            if self.coder != "lasso_lars" or self.compat == "shipped_onmf":
+                raise ValueError("multi-GPU training uses the lasso_lars coder with accumulating aggregates")
+            W, A0, B0, _ = _host.broadcast_run_inputs(group, dev, d, r, W, A0, B0, None)
+        eng = self._engine(d, r, track_C=want_C, group=group)
         eng.set_state(W, A0, B0, C0)
         shipped = self.compat == "shipped_onmf"
         if shipped:
             A_init, B_init = eng.A.clone(), eng.B.clone()
             C_init = eng.C.clone() if want_C else None
-        Xb = torch.empty(self.batch_size if self.subsample else 0, d, dtype=self._dtype, device=dev)
+        m = self.batch_size if self.subsample else n
+        lo, hi = shard_range(m, world, rank)
+        Xb = torch.empty(hi - lo, d, dtype=self._dtype, device=dev) if self.subsample else None
+        # lasso coder: nothing but the minibatch draw touches the global RNG inside the loop, so all steps' indices are
+        # drawn up front (same stream as src/onmf.py:212 step by step) and uploaded once; the PGD coder interleaves its
+        # H0 = np.random.rand(r, n) draws (src/onmf.py:245-246) and keeps the per-step order.
+        idx_all = idx_dev = None
+        if self.subsample and self.coder == "lasso_lars" and self.iterations > 1:
+            idx_all = np.stack([np.random.randint(n, size=self.batch_size) for _ in range(int(self.iterations) - 1)])
+            if world > 1:
+                idx_all = _host.broadcast_indices(group, dev, idx_all)
+            idx_dev = _host.upload_indices(idx_all[:, lo:hi], dev)
         for i in np.arange(1, self.iterations):
             idx = np.arange(n)
             if self.subsample:
-                idx = np.random.randint(n, size=self.batch_size)          # src/onmf.py:212
-                _lib.gather_rows(pool, torch.from_numpy(idx.astype(np.int64)).to(dev), Xb)
+                if idx_all is not None:
+                    idx = idx_all[i - 1]
+                    _lib.gather_rows(pool, idx_dev[i - 1], Xb)
+                else:
+                    idx = np.random.randint(n, size=self.batch_size)      # src/onmf.py:212
+                    _lib.gather_rows(pool, _host.upload_indices(idx, dev), Xb)
                 Xt = Xb
             else:
-                Xt = pool
+                Xt = pool[lo:hi]
             if shipped:
-                # src/onmf.py:217 re-binds the aggregates to the arrays fixed before the loop
-                eng.flush()
-                eng.A.copy_(A_init)
-                eng.B.copy_(B_init)
-                if want_C:
-                    eng.C.copy_(C_init)
+                # src/onmf.py:217 re-binds the aggregates to the arrays fixed before the loop.  reset_aggregates orders the
+                # copies behind the previous step's blend AND the next dictionary update behind the copies.
+                eng.reset_aggregates(A_init, B_init, C_init)
             Ht = self._step_device(eng, Xt, float(t0 + i))
             self.history = np.float64(t0 + i) + 1
-            code[:, idx] += _host.from_sample_major(Ht)               # src/onmf.py:221
+            code[:, idx[lo:hi]] += _host.from_sample_major(Ht)        # src/onmf.py:221 (this rank's columns)
         Wd, Ad, Bd, Cd = eng.state()
         self.lars_stats = eng.read_stats()
         Wn, An, Bn = _host.to_numpy(Wd), _host.to_numpy(Ad), _host.to_numpy(Bd)

@@ -15,7 +15,13 @@ The random draws (W0 = np.random.rand(d, r), idx = np.random.randint(n, size=bat
 global RNG on the host in the reference's order (src/ontf.py:213, :230), so a seeded run sees the same
 initial dictionary and minibatch sequence as the reference.  Everything else runs on the GPU.
 
-Extra keyword (not in the reference): precision = "fp32" (production, default) | "fp64" (parity mode).
+Extra keywords (not in the reference):
+  precision     = "fp32" (production, default) | "fp64" (parity mode)
+  process_group = a torch.distributed group (default: the WORLD group when torch.distributed is initialised with more
+                  than one rank, else single GPU).  Every rank constructs the object with the same X and calls
+                  train_dict_single(); rank 0's random draws (W0 and the minibatch indices) are broadcast, each rank
+                  codes its contiguous shard of every minibatch (parallel.shard_range), the packed partial sums are
+                  all-reduced, and every rank returns the identical (W, A, B)  [src/ontf.py:156-244 data-parallel].
 """
 from __future__ import annotations
 
@@ -24,6 +30,7 @@ import torch
 
 from . import _host, _lib
 from .engine import OnmfEngine
+from .parallel import default_group, shard_range
 
 DEBUG = False
 
@@ -44,7 +51,8 @@ class Online_NTF():
                  alpha=None,
                  beta=None,
                  subsample=True,
-                 precision=None):
+                 precision=None,
+                 process_group=None):
         self.X = X
         self.n_components = n_components
         self.batch_size = batch_size
@@ -63,14 +71,24 @@ class Online_NTF():
         self.precision = precision
         self._dtype = _host.torch_dtype(precision)
         self.lars_stats = None
+        self.process_group = process_group
+        self._engines = {}
 
     # -- helpers ---------------------------------------------------------------------------------
     def _alpha(self):
         return 2 if self.alpha is None else self.alpha       # src/ontf.py:79-81
 
-    def _engine(self, d, r, collect_stats=False):
-        return OnmfEngine(d, r, alpha=self._alpha(), beta=self.beta, dtype=self._dtype,
-                          device=_host.device(), collect_stats=collect_stats)
+    def _engine(self, d, r, collect_stats=False, group=None):
+        """One engine (streams, step plan, workspaces) per (d, r, group) is kept on the object: drivers call
+        step() / joint_sparse_code_tensor() / update_dict() once per patch or per epoch."""
+        key = (int(d), int(r), id(group) if group is not None else None)
+        eng = self._engines.get(key)
+        if eng is None or eng.alpha != float(self._alpha()) or eng.beta != (1.0 if self.beta is None else float(self.beta)):
+            eng = OnmfEngine(d, r, alpha=self._alpha(), beta=self.beta, dtype=self._dtype,
+                             device=_host.device(), collect_stats=True, process_group=group)
+            self._engines[key] = eng
+        eng.stats.zero_()
+        return eng
 
     def _unfold_sample_major(self, dev):
         """Matricize self.X (src/ontf.py:203-208) directly into the sample-major device layout (n x d).
@@ -91,7 +109,7 @@ class Online_NTF():
         dev = _host.device()
         Xt = _host.to_sample_major(X, self._dtype, dev)
         Wd = _host.to_device(W, self._dtype, dev)
-        eng = self._engine(Wd.shape[0], Wd.shape[1], collect_stats=True)
+        eng = self._engine(Wd.shape[0], Wd.shape[1])
         Ht = eng.sparse_code(Xt, Wd)
         H = Ht.detach().to(torch.float64).cpu().numpy()
         self.lars_stats = eng.read_stats()
@@ -134,17 +152,29 @@ class Online_NTF():
             W, A, B = self.initial_dict, self.initial_A, self.initial_B
         t0 = self.history
 
-        eng = self._engine(d, r, collect_stats=True)
+        group, world, rank = default_group(self.process_group)
+        steps = max(int(self.iterations) - 1, 0)
+        # The reference draws idx = np.random.randint(n, size=batch) once per step (src/ontf.py:230) and nothing else
+        # touches the global RNG inside the loop (lasso_lars draws nothing), so drawing all steps up front is the same
+        # stream; the indices go to the device in ONE pinned, asynchronous copy instead of one blocking copy per step.
+        idx_all = None
+        if self.subsample and steps > 0:
+            idx_all = np.stack([np.random.randint(n, size=self.batch_size) for _ in range(steps)]).astype(np.int64)
+        if world > 1:
+            W, A, B, idx_all = _host.broadcast_run_inputs(group, dev, d, r, W, A, B, idx_all)
+        eng = self._engine(d, r, group=group)
         eng.set_state(W, A, B)
-        Xb = torch.empty(self.batch_size if self.subsample else n, d, dtype=self._dtype, device=dev)
-        for i in np.arange(1, self.iterations):
+        m = self.batch_size if self.subsample else n
+        lo, hi = shard_range(m, world, rank)           # this rank's columns of every minibatch (contiguous block)
+        idx_d = _host.upload_indices(idx_all[:, lo:hi], dev) if idx_all is not None else None
+        Xb = torch.empty(hi - lo, d, dtype=self._dtype, device=dev) if self.subsample else None
+        for s_ in range(steps):
+            i = s_ + 1
             if self.subsample:
-                idx = np.random.randint(n, size=self.batch_size)       # src/ontf.py:230
-                idx_d = torch.from_numpy(idx.astype(np.int64)).to(dev)
-                _lib.gather_rows(pool, idx_d, Xb)
+                _lib.gather_rows(pool, idx_d[s_], Xb)                  # X_batch = X_unfold[:, idx], src/ontf.py:231
                 Xt = Xb
             else:
-                Xt = pool
+                Xt = pool[lo:hi]
             eng.step(Xt, float(t0 + i))
             self.history = np.float64(t0 + i) + 1
         Wd, Ad, Bd, _ = eng.state()

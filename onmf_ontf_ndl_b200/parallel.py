@@ -15,6 +15,19 @@ def shard_range(n: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def default_group(process_group=None):
+    """(group, world, rank) for the reference-facing classes: an explicit group, else the WORLD group when
+    torch.distributed is initialised with more than one rank, else single process."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None, 1, 0
+    group = process_group if process_group is not None else dist.group.WORLD
+    world = dist.get_world_size(group)
+    if world <= 1:
+        return None, 1, 0
+    return group, world, dist.get_rank(group)
+
+
 def pack_partial(HtH, HtX):
     """[HtH | HtX] -> one (k x (k+d)) buffer (what gets all-reduced)."""
     import torch

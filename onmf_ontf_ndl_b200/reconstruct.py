@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _host, _lib
+from . import _host, _lib, patches
 from .engine import OnmfEngine
 
 
@@ -80,3 +80,73 @@ def reconstruct_image(A, W, patch_size, recons_resolution=1, alpha=1, sub_iter=1
     if return_code:
         res = res + (_host.from_sample_major(Ht),)
     return res
+
+
+def reconstruct_network(G, W, embs, alpha=0, precision=None):
+    """Batched form of Network_Reconstructor.reconstruct_network (network_reconstruction_nx.py:444-511).
+
+    The reference walks the motif MCMC and, per step, builds ONE k x k adjacency patch (`get_single_patch_glauber`,
+    :331-340), codes it with `SparseCoder(transform_alpha=0, 'lasso_lars', positive_code=True)` (:466-473), forms
+    patch_recons = W code (:474-475) and folds every entry into a running-mean weight of the directed edge
+    (emb[q], emb[r]) (:477-491).  The walk is sequential and stays with the caller; given its states `embs`
+    (recons_iter x k node labels, the embedding AFTER each update, i.e. what get_single_patch_glauber returns), this
+    runs all steps at once: K1 motif patches -> K2 Gram/covariances -> K3 positive LARS at alpha -> Ht W^T -> one
+    scatter kernel accumulating sum / count per directed pair.
+
+    G: networkx graph (or scipy sparse adjacency, node labels = indices); W: (k*k, r) dictionary.
+    Returns (pairs (E x 2 node labels), weight (E,), count (E,)) sorted by (a, b) position in G.nodes -- the content
+    of the reference's G_recons / G_overlap_count DiGraphs."""
+    dev = _host.device()
+    dtype = _host.torch_dtype(precision)
+    W = np.asarray(W, dtype=np.float64)
+    d, r = W.shape
+    embs = np.asarray(embs)
+    n, kk = embs.shape
+    if kk * kk != d:
+        raise ValueError("dictionary has %d rows, expected k^2 = %d" % (d, kk * kk))
+    rowptr, colidx, nodes = patches.graph_to_csr(G)
+    pos = {u: i for i, u in enumerate(nodes)}
+    emb_i = np.asarray([[pos[u] for u in row] for row in embs.tolist()], dtype=np.int32).reshape(n, kk)
+    e = torch.from_numpy(emb_i).to(dev)
+    Xt = torch.empty(n, d, dtype=dtype, device=dev)
+    if n:
+        _lib.motif_patches(torch.from_numpy(np.asarray(rowptr, dtype=np.int64)).to(dev),
+                           torch.from_numpy(np.asarray(colidx, dtype=np.int32)).to(dev), e, Xt)      # K1
+    Wd = _host.to_device(W, dtype, dev)
+    eng = OnmfEngine(d, r, alpha=alpha, dtype=dtype, device=dev)
+    Ht = eng.sparse_code(Xt, Wd, alpha=alpha)                                                        # K2 + K3
+    Wt = torch.empty(r, d, dtype=dtype, device=dev)
+    _lib.transpose(Wd, Wt)
+    R = torch.empty(n, d, dtype=dtype, device=dev)
+    if n:
+        _lib.cov(Ht, Wt, R)                                                                          # patch_recons rows
+    cap = 1
+    while cap < 2 * max(n * d, 1) + 2:
+        cap *= 2
+    keys = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+    sums = torch.zeros(cap, dtype=torch.float64, device=dev)
+    cnts = torch.zeros(cap, dtype=torch.int32, device=dev)
+    failed = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.edge_scatter_add(R, e, keys, sums, cnts, failed)
+    if int(failed.item()):
+        raise _lib.OnmfKernelError("edge_scatter_add could not place %d entries" % int(failed.item()))
+    used = torch.nonzero(cnts > 0).flatten()
+    kz = keys[used].cpu().numpy().astype(np.uint64)
+    sm = sums[used].cpu().numpy()
+    ct = cnts[used].cpu().numpy().astype(np.int64)
+    order = np.argsort(kz, kind="stable")
+    kz, sm, ct = kz[order], sm[order], ct[order]
+    a, b = (kz >> np.uint64(32)).astype(np.int64), (kz & np.uint64(0xffffffff)).astype(np.int64)
+    lab = np.asarray(nodes, dtype=object)
+    pairs = np.stack([lab[a], lab[b]], axis=1) if len(kz) else np.empty((0, 2), dtype=object)
+    return pairs, sm / np.maximum(ct, 1), ct
+
+
+def simple_graph_edges(pairs, weight):
+    """The reference's final rounding (network_reconstruction_nx.py:499-507): undirected edge {a, b} when the mean
+    weight of the directed pair rounds to a positive integer.  Returns a set of frozensets."""
+    out = set()
+    for (a, b), w in zip(pairs.tolist(), np.asarray(weight).tolist()):
+        if np.round(w) > 0:
+            out.add(frozenset((a, b)))
+    return out

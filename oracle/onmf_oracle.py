@@ -385,3 +385,29 @@ def motif_patches(adj_sets, emb):
             for r in range(k):
                 X[q * k + r, j] = 1.0 if emb[j, r] in adj_sets[emb[j, q]] else 0.0
     return X
+
+
+def reconstruct_network_loop(adj_sets, W, embs, alpha=0.0, coder=None):
+    """network_reconstruction_nx.py:464-491 restated: per MCMC state one k x k adjacency patch (has_edge of the embedded
+    nodes, :302-305), coded with the positive lasso_lars at `alpha` (:466-473), patch_recons = W code (:474-475), every
+    entry folded into a running mean per DIRECTED pair (emb[q], emb[r]) in loop order (:477-491).
+    adj_sets: {node: set(neighbours)}; embs: (T x k) node labels.  Returns ({(a, b): weight}, {(a, b): count})."""
+    embs = np.asarray(embs)
+    kk = embs.shape[1]
+    if coder is None:
+        coder = lambda patch: sparse_code_lars(patch, W, alpha)
+    weight, count = {}, {}
+    for emb in embs.tolist():
+        patch = np.zeros((kk * kk, 1))
+        for q in range(kk):
+            for r in range(kk):
+                patch[q * kk + r, 0] = 1.0 if emb[r] in adj_sets.get(emb[q], ()) else 0.0
+        code = coder(patch)                                   # (r x 1)
+        rec = (W @ code).reshape(kk, kk)
+        for q in range(kk):
+            for r in range(kk):
+                key = (emb[q], emb[r])
+                j = count.get(key, 0)
+                weight[key] = (j * weight[key] + rec[q, r]) / (j + 1) if j else rec[q, r]
+                count[key] = j + 1
+    return weight, count

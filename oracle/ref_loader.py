@@ -70,3 +70,45 @@ def load_reference():
         spec.loader.exec_module(mod)
         mods.append(mod)
     return tuple(mods)
+
+
+def load_reference_driver(name):
+    """Import one of the reference's top-level driver scripts (e.g. "network_reconstruction_nx",
+    "image_reconstruction_tensor") UNMODIFIED, bound to the reference's own `src` package.  Non-arithmetic imports that
+    are not installed here (seaborn, matplotlib, skimage, progressbar, tensorly) are stubbed; `utils.onmf` / `utils.ontf`
+    (a package the reference imports but does not ship) are aliased to its `src.onmf` / `src.ontf`."""
+    import importlib
+    import importlib.util
+    onmf, ontf = load_reference()
+    try:
+        import matplotlib.image  # noqa: F401
+    except Exception:
+        sys.modules["matplotlib"].image = _stub("matplotlib.image")
+    for nm in ("seaborn",):
+        try:
+            importlib.import_module(nm)
+        except Exception:
+            _stub(nm)
+    try:
+        import skimage.transform  # noqa: F401
+    except Exception:
+        sk = _stub("skimage")
+        sk.transform = _stub("skimage.transform", downscale_local_mean=None)
+    saved = {k: sys.modules.get(k) for k in ("src", "src.onmf", "src.ontf", "utils", "utils.onmf", "utils.ontf")}
+    try:
+        pkg = types.ModuleType("src"); pkg.__path__ = []
+        upkg = types.ModuleType("utils"); upkg.__path__ = []
+        pkg.onmf, pkg.ontf, upkg.onmf, upkg.ontf = onmf, ontf, onmf, ontf
+        sys.modules.update({"src": pkg, "src.onmf": onmf, "src.ontf": ontf, "utils": upkg, "utils.onmf": onmf,
+                            "utils.ontf": ontf})
+        spec = importlib.util.spec_from_file_location("_reference_driver_" + name,
+                                                      os.path.join(REFERENCE_ROOT, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod

@@ -63,3 +63,35 @@ def test_two_ranks_match_single_rank():
     out = mgr.dict()
     mp.spawn(_run, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1], dict(out)
+
+
+# ---------------------------------------------------------------------------------------------- through the reference-facing classes
+def test_class_api_two_ranks_gloo_one_device(golden_dir):
+    """Online_NTF.train_dict_single / Online_NMF.train_dict with torch.distributed initialised (two gloo ranks sharing
+    cuda:0): rank 0's draws are broadcast, minibatches shard by columns, every rank returns the golden single-process
+    result and bit-identical dictionaries."""
+    import tests._mr_class_worker as wk
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(wk._spawn_entry, args=(2, port, golden_dir, out), nprocs=2, join=True)
+    for r in (0, 1):
+        assert all(v["ok"] for v in out[r].values()), dict(out)
+
+
+def test_class_api_two_ranks_nccl_two_devices(golden_dir, tmp_path):
+    """the same under torchrun with NCCL on two devices (skipped on a one-GPU box)."""
+    import subprocess
+    import sys
+    import json
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "_mr_class_worker.py"), golden_dir, str(tmp_path)]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for rank in (0, 1):
+        res = json.load(open(os.path.join(str(tmp_path), "rank%d.json" % rank)))
+        assert all(v["ok"] for v in res.values()), res

@@ -436,7 +436,7 @@ def test_patch_grid_mean_equals_sklearn_overlap_average():
 # ---------------------------------------------------------------------------------------------- full-length runs, fp32 bars
 @pytest.mark.parametrize("name", ["full_cfg1", "full_cfg2", "full_cfg3", "full_cfg4"])
 def test_full_length_run_fp32_bars(golden_dir, name):
-    """BASELINE.json configs at full minibatch size (cfg1 also at its full 100 iterations) in the fp32 production mode:
+    """BASELINE.json configs at full minibatch size for 100 / 100 / 25 / 25 iterations in the fp32 production mode:
     final dictionary per atom within 1e-3 of the reference's, reconstruction error within 0.5 %."""
     g = load(golden_dir, name)
     scale = 255.0 if name in ("full_cfg1", "full_cfg2") else 1.0
@@ -591,3 +591,160 @@ def test_fused_step_equals_python_composed_schedule():
             for a, b in zip(res[0][:5], res[1][:5]):
                 assert (a is None and b is None) or torch.equal(a, b)
             assert res[0][5] == res[1][5]                            # same launch accounting
+
+
+# ---------------------------------------------------------------------------------------------- the benchmarked config (cfg5)
+def _cfg5_inputs(g):
+    ntr = int(g["n_train"])
+    X = np.random.RandomState(int(g["x_seed"])).rand(1024, ntr + int(g["n_holdout"]))
+    W0 = np.random.RandomState(int(g["seed"])).rand(1024, int(g["k"]))
+    assert abs(W0.sum() - float(g["W0_checksum"])) < 1e-9
+    return X, W0, ntr
+
+
+def test_cfg5_per_step_codes_on_learned_dictionaries(golden_dir):
+    """d=1024, k=256 (the shape bench.py times), 10 steps of the reference at minibatch 2048 (fixture full_cfg5).
+
+    fp64 engine: per-step codes against the reference's lasso_lars codes at EVERY step (<= 1e-8), final W / A / B.
+    fp32 production path (tensor-core products, fused onmf_step, hybrid 64-slot first tier): at every step >= 2 the fp32
+    engine is put on the trajectory's state (W, A, B from the fp64 engine, which equals the reference's to ~1e-9) and
+    codes the same minibatch through OnmfEngine.step; codes within 2e-3, no column may leave the first tier
+    (overflow == 0) -- this is the regime the benchmark runs in (unit-norm learned dictionary, mean active set ~16)."""
+    g = load(golden_dir, "full_cfg5")
+    X, W0, ntr = _cfg5_inputs(g)
+    k, iters = int(g["k"]), int(g["iters"])
+    pool64 = tt(X[:, :ntr].T, torch.float64)
+    pool32 = pool64.float().contiguous()
+    e64 = OnmfEngine(1024, k, alpha=1.0, dtype=torch.float64, device=dev(), collect_stats=True)
+    e32 = OnmfEngine(1024, k, alpha=1.0, dtype=torch.float32, device=dev(), collect_stats=True, use_tc=True, fused=True)
+    assert e32.use_tc and e32.fused
+    e64.set_state(W0)
+    nb = g["idx"].shape[1]
+    xb64 = torch.empty(nb, 1024, dtype=torch.float64, device=dev())
+    xb32 = torch.empty(nb, 1024, dtype=torch.float32, device=dev())
+    worst32 = 0.0
+    for i in range(iters):
+        idx = torch.from_numpy(g["idx"][i].astype(np.int64)).to(dev())
+        Href = g["H_%d" % i]                                   # (n x r)
+        if i >= 2:
+            Wc, Ac, Bc, _ = e64.state()
+            e32.set_state(Wc, Ac, Bc)
+            e32.stats.zero_()
+            _lib.gather_rows(pool32, idx, xb32)
+            H32 = e32.step(xb32, float(i + 1)).cpu().numpy().astype(np.float64)
+            st = e32.read_stats()
+            assert st["overflow"] == 0 and st["columns"] == nb and st["flagged"] == 0, (i, st)
+            assert st["max_active"] <= 64
+            worst32 = max(worst32, rel(H32, Href))
+            assert rel(H32, Href) < CODE_TOL_FP32, (i, rel(H32, Href))
+        _lib.gather_rows(pool64, idx, xb64)
+        H64 = e64.step(xb64, float(i + 1)).cpu().numpy()
+        assert rel(H64, Href) < CODE_TOL_FP64, (i, rel(H64, Href))
+    W, A, B, _ = e64.state()
+    torch.cuda.synchronize()
+    assert per_atom(W.cpu().numpy(), g["W"]) < 1e-8 and rel(A.cpu().numpy(), g["A"]) < 1e-8 and rel(B.cpu().numpy(), g["B"]) < 1e-8
+    assert e64.read_stats()["flagged"] == 0
+
+
+def test_cfg5_full_run_fp32_bars(golden_dir):
+    """the same 10-step run end to end in the fp32 production mode through the reference-facing class: final dictionary per
+    atom within 1e-3, A / B within 2e-3, held-out reconstruction error within 0.5 % (north_star bars at the benchmarked
+    shape)."""
+    g = load(golden_dir, "full_cfg5")
+    X, W0, ntr = _cfg5_inputs(g)
+    np.random.seed(int(g["seed"]))
+    m = Online_NTF(X[:, :ntr, None], n_components=int(g["k"]), iterations=int(g["iters"]) + 1, batch_size=int(g["batch"]),
+                   alpha=1.0, mode=0, learn_joint_dict=False, precision="fp32")
+    W, A, B, _ = m.train_dict_single()
+    assert float(m.history) == float(g["history"])
+    assert per_atom(W, g["W"]) < ATOM_TOL_FP32, per_atom(W, g["W"])
+    assert rel(A, g["A"]) < 2e-3 and rel(B, g["B"]) < 2e-3
+    Xe = X[:, ntr:]
+    e_got = np.linalg.norm(Xe - W @ O.sparse_code_sklearn(Xe, W, 1.0)) / np.linalg.norm(Xe)
+    assert abs(e_got - float(g["recon"])) <= RECON_TOL * float(g["recon"])
+    assert m.lars_stats["flagged"] <= m.lars_stats["columns"] // 1000
+
+
+# ---------------------------------------------------------------------------------------------- shipped re-binding + lasso coder
+def test_shipped_rebinding_with_lasso_coder(golden_dir):
+    """compat='shipped_onmf' (src/onmf.py:217: every step starts from the INITIAL aggregates) combined with the lasso coder:
+    the dictionary update runs on the side stream and must see the re-copied A, B (OnmfEngine.reset_aggregates orders the
+    copies and re-marks the state) -- compared with the same recursion on the oracle."""
+    g = load(golden_dir, "cfg1_renoir_gray")
+    X = g["X"][:, :500]
+    W0, A0, B0 = g["W_3"], g["A_3"], g["B_3"]
+    for prec, tol in (("fp64", 1e-8), ("fp32", 1e-3)):
+        np.random.seed(17)
+        m = Online_NMF(X, n_components=25, iterations=6, batch_size=120, ini_dict=W0, ini_agg=[A0, B0], history=4, alpha=1,
+                       subsample=True, compat="shipped_onmf", coder="lasso_lars", precision=prec)
+        W, agg, code = m.train_dict()
+        rs = np.random.RandomState(17)
+        Wr, A1, B1 = W0, A0, B0
+        for i in range(1, 6):
+            ii = rs.randint(500, size=120)
+            H = c_oracle.sparse_code(X[:, ii], Wr, 1.0)
+            A1, B1 = O.aggregate(A0, B0, H, X[:, ii], float(4 + i))       # blend from the INITIAL aggregates
+            Wr = O.update_dict(Wr, A0, B0)                                # update with the INITIAL aggregates
+        assert per_atom(W, Wr) < tol and rel(agg[0], A1) < tol and rel(agg[1], B1) < tol, prec
+        assert float(m.history) == 10.0
+
+
+def test_online_nmf_alpha_none_follows_the_coder():
+    X = np.random.rand(12, 30)
+    assert Online_NMF(X)._alpha() == 2                                    # lasso_lars: src/ontf.py:79-81
+    assert Online_NMF(X, coder="pgd")._alpha() == 0 and Online_NMF(X, compat="shipped_onmf")._alpha() == 0   # src/onmf.py:82-84
+    assert Online_NMF(X, alpha=0.5)._alpha() == 0.5
+
+
+# ---------------------------------------------------------------------------------------------- batched network reconstruction (§8f.1)
+def test_batched_network_reconstruction_matches_reference(golden_dir):
+    """all MCMC states of a trajectory at once (motif patches -> alpha=0 LARS -> W h -> scatter-mean) against the weights
+    and overlap counts of the UNMODIFIED Network_Reconstructor.reconstruct_network (network_reconstruction_nx.py:444-511)."""
+    import networkx as nx
+    from onmf_ontf_ndl_b200 import reconstruct_network
+    from onmf_ontf_ndl_b200.reconstruct import simple_graph_edges
+    g = load(golden_dir, "network_recons")
+    G = nx.Graph()
+    G.add_nodes_from(range(int(g["n_nodes"])))
+    G.add_edges_from(g["graph_edges"].tolist())
+    for prec, tol in (("fp64", 1e-9), ("fp32", 2e-3)):
+        pairs, weight, count = reconstruct_network(G, g["W"], g["embs"], alpha=0, precision=prec)
+        assert np.array_equal(np.asarray(pairs.tolist()), g["pairs"]) and np.array_equal(count, g["count"])
+        assert np.max(np.abs(weight - g["weight"])) < tol * max(1.0, np.abs(g["weight"]).max()), prec
+    assert simple_graph_edges(pairs, weight) == {frozenset(e) for e in g["simple_edges"].tolist()}
+    # empty trajectory
+    p0, w0, c0 = reconstruct_network(G, g["W"], np.empty((0, 6), dtype=np.int64))
+    assert len(p0) == 0 and len(w0) == 0
+
+
+# ---------------------------------------------------------------------------------------------- robustness of the gathers / large shapes
+def test_gather_index_checks_and_large_dictionary_fallbacks():
+    pool = torch.rand(10, 8, device=dev())
+    idx = torch.tensor([0, 9, 10, -1, 3], dtype=torch.int64, device=dev())
+    out = torch.zeros(5, 8, device=dev())
+    _lib.gather_rows(pool, idx, out)
+    assert torch.equal(out[0], pool[0]) and torch.equal(out[1], pool[9]) and torch.equal(out[4], pool[3])
+    assert torch.isnan(out[2]).all() and torch.isnan(out[3]).all()                 # bad indices: NaN rows, no wild reads
+    hi, lo = torch.zeros(5, 8, device=dev()), torch.zeros(5, 8, device=dev())
+    _lib.gather_rows_split(pool, idx, hi, lo)
+    assert torch.isnan(hi[2]).all() and torch.equal(hi[1] + lo[1], pool[9])
+    img = torch.rand(12, 9, device=dev())
+    co = torch.tensor([[0, 0], [8, 5], [9, 0], [0, 6], [-1, 2]], dtype=torch.int32, device=dev())
+    P = torch.zeros(5, 16, device=dev())
+    _lib.gather_patches(img, co, 4, P)
+    assert torch.equal(P[1], img[8:12, 5:9].reshape(-1)) and torch.isnan(P[2]).all() and torch.isnan(P[3]).all() and torch.isnan(P[4]).all()
+    # dictionary update beyond one cluster's shared memory: cooperative-grid fallback == oracle
+    rng = np.random.default_rng(4)
+    d, k = 20000, 64
+    assert _lib.update_dict_workspace(torch.float64, d, k) > 0 and _lib.update_dict_workspace(torch.float32, 1024, 256) == 0
+    W = rng.random((d, k)); H = rng.random((k, 50))
+    A, B = H @ H.T / 7, H @ rng.random((50, d)) / 7
+    for dt_, tol in ((torch.float64, 1e-12), (torch.float32, 1e-3)):
+        out = torch.empty(d, k, dtype=dt_, device=dev())
+        _lib.update_dict(tt(W, dt_), tt(A, dt_), tt(B, dt_), out)
+        assert per_atom(out.cpu().numpy().astype(np.float64), O.update_dict(W, A, B)) < tol
+    # projected-gradient coder with a Gram beyond shared memory (k = 300 > 238): read through L1/L2
+    d, k, n = 64, 300, 40
+    Wp = rng.random((d, k)); Xp = rng.random((d, n)); H0 = rng.random((k, n))
+    H = update_code_within_radius(Xp, Wp, H0=H0, r=None, alpha=0.5, sub_iter=3, stopping_diff=0.0, precision="fp64")
+    assert rel(H, O.update_code_within_radius(Xp, Wp, H0.copy(), r=None, alpha=0.5, sub_iter=3, stopping_diff=0.0)) < 1e-10

@@ -155,3 +155,44 @@ def test_reconstruction_loop_golden(golden_dir):
     rec, cnt, codes = O.reconstruct_image_loop(g["img"], g["W"], int(g["patch"]), int(g["stride"]), 1, 10, 0.01, g["H0"])
     assert rel(codes, g["codes"]) < 1e-12 and rel(rec, g["recons"]) < 1e-12 and np.array_equal(cnt, g["count"])
     assert cnt.max() == 9 and cnt[-1, -1] == 0          # the loop never reaches the last row/column (range(0, H-k, res))
+
+
+def test_full_cfg5_every_step(golden_dir):
+    """the benchmarked shape (d=1024, k=256) on the learned dictionaries of a 10-step reference run: the restated LARS (C)
+    reproduces the reference's codes at every step (192 columns per step; the aggregation uses the reference's full code
+    matrix so that all ten dictionaries are exactly the reference's), and the restated A/B recursion + dictionary
+    update reproduce the final state."""
+    g = load(golden_dir, "full_cfg5")
+    ntr, k = int(g["n_train"]), int(g["k"])
+    X = np.random.RandomState(int(g["x_seed"])).rand(1024, ntr + int(g["n_holdout"]))
+    W = np.random.RandomState(int(g["seed"])).rand(1024, k)
+    assert abs(W.sum() - float(g["W0_checksum"])) < 1e-9
+    A, B = np.zeros((k, k)), np.zeros((k, 1024))
+    for i in range(int(g["iters"])):
+        Xb = X[:, g["idx"][i]]
+        Href = g["H_%d" % i].T                       # fixture stores the reference's H1 (n x r)
+        H = c_oracle.sparse_code(Xb[:, :192], W, 1.0)
+        assert rel(H, Href[:, :192]) < 1e-9, i
+        A1, B1 = O.aggregate(A, B, Href, Xb, float(i + 1))
+        W = O.update_dict(W, A, B)
+        A, B = A1, B1
+    assert rel(W, g["W"]) < 1e-9 and rel(A, g["A"]) < 1e-9 and rel(B, g["B"]) < 1e-9
+    assert float(g["history"]) == int(g["iters"]) + 1
+
+
+def test_network_reconstruction_golden(golden_dir):
+    """oracle restatement of the per-step reconstruction loop (network_reconstruction_nx.py:464-491) against the weights /
+    overlap counts the UNMODIFIED driver method produced (oracle/make_golden.py, fixture network_recons)."""
+    g = load(golden_dir, "network_recons")
+    adj = {}
+    for a, b in g["graph_edges"].tolist():
+        adj.setdefault(a, set()).add(b)
+        adj.setdefault(b, set()).add(a)
+    W = g["W"]
+    w, c = O.reconstruct_network_loop(adj, W, g["embs"], 0.0, coder=lambda p: c_oracle.sparse_code(p, W, 0.0))
+    pairs = [tuple(p) for p in g["pairs"].tolist()]
+    assert sorted(w.keys()) == pairs
+    assert max(abs(w[p] - x) for p, x in zip(pairs, g["weight"].tolist())) < 1e-12
+    assert all(c[p] == x for p, x in zip(pairs, g["count"].tolist()))
+    simple = {frozenset(p) for p, x in w.items() if np.round(x) > 0}
+    assert simple == {frozenset(e) for e in g["simple_edges"].tolist()}
