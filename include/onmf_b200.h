@@ -69,6 +69,18 @@ int onmf_gather_patches(int dtype, const void* img, int H, int Wd, int C, const 
 int onmf_gather_rows(int dtype, const void* pool, int64_t n_pool, int d, const int64_t* idx,
                      int64_t n, void* Xt, void* stream);
 
+/* storage formats of a streamed minibatch (arithmetic is always fp32 / fp64): the reference's image data is 8-bit before
+ * `data / 255` (image_reconstruction.py:88), so host-resident patches can cross PCIe as u8 (4x fewer bytes) or fp16.
+ * dst[i] = (float)src[i] * scale for i < count (count % 4 == 0); with lo != NULL the result is written as the TF32 hi/lo
+ * pair of the tensor-core path (dst = hi). */
+#define ONMF_STORE_U8 2
+#define ONMF_STORE_F16 3
+int onmf_widen(int src_kind, const void* src, int64_t count, double scale, void* dst, void* lo, void* stream);
+
+/* elementwise precision change f32 <-> f64 (used to run the coder in FP64 on the covariances of the fp32 path for the one
+ * minibatch that is coded against a raw, unnormalised initial dictionary; see OnmfEngine._code_wide) */
+int onmf_convert(int dtype_in, int dtype_out, const void* src, int64_t count, void* dst, void* stream);
+
 /* transpose/convert a (d x n) row-major matrix (the reference's X layout, any of f32/f64) into the
  * sample-major (n x d) layout in `dtype_out`.  Also used for H (k x n) <-> Ht. */
 int onmf_transpose(int dtype_in, int dtype_out, const void* src, int64_t rows, int64_t cols,
@@ -153,6 +165,9 @@ int onmf_surrogate_partial(int dtype, const void* Ht, const void* Xt, int64_t n,
                            void* stream);
 int onmf_surrogate_blend(int dtype, const void* P, int k, int d, double w, void* A, void* B,
                          void* stream);
+/* same with the weight read from device memory (one double): the form a captured CUDA graph of the step replays */
+int onmf_surrogate_blend_dev(int dtype, const void* P, int k, int d, const double* w_dev, void* A, void* B,
+                             void* stream);
 /* optional d x d aggregate: Cagg = (1-w) Cagg + w Xt^T Xt   (single rank; P2 is a d x d scratch) */
 int onmf_xxt_partial(int dtype, const void* Xt, int64_t n, int d, void* P2, void* workspace,
                      size_t workspace_bytes, void* stream);
@@ -181,6 +196,26 @@ size_t onmf_surrogate_tc_workspace(int64_t n, int k, int d);
 int onmf_surrogate_partial_tc(const void* Ht_hi, const void* Ht_lo, const void* Xt_hi, const void* Xt_lo,
                               int64_t n, int k, int d, void* P, void* workspace, size_t workspace_bytes,
                               void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1 + K2 and K4 fused on the tensor cores (fp32, k <= 256): the minibatch is read ONCE per product, as stored.
+ * Loader warps read the minibatch rows straight from the resident pool through the minibatch indices -- fp32, or the narrow
+ * storage formats ONMF_STORE_U8 / ONMF_STORE_F16 (value = stored * scale) -- split them into TF32 hi / lo in registers and
+ * write the swizzled UMMA operand tiles in shared memory; no hi/lo copy of the minibatch or of the codes ever exists in HBM.
+ *   pool (n_pool x ld_pool, one sample per row), idx (n int64 row indices, or NULL for rows 0..n-1)
+ *   onmf_cov_fused_tc       : Ct (n x k) = X[idx] W                                   (W_hi / W_lo: onmf_split_tf32 of W)
+ *   onmf_surrogate_fused_tc : P (k x (k+d)) = [Ht^T Ht | Ht^T X[idx]]  (P may be NULL when blend != 0)
+ *                             blend != 0 (single GPU): A <- (1-w) A + w P_A, B <- (1-w) B + w P_B in the same pass, w from
+ *                             *w_dev (device double) when w_dev != NULL, else the host value w
+ * Persistent CTAs (one per SM), FP32 accumulators in tensor memory, fixed-order reductions (deterministic).
+ * ------------------------------------------------------------------------------------------- */
+int onmf_fused_tc_supported(int k, int d);
+int onmf_cov_fused_tc(int src_kind, const void* pool, int64_t n_pool, int64_t ld_pool, const int64_t* idx, int64_t n,
+                      int d, double scale, const void* W_hi, const void* W_lo, int k, void* Ct, void* stream);
+size_t onmf_surrogate_fused_tc_workspace(int64_t n, int k, int d);
+int onmf_surrogate_fused_tc(const void* Ht, int src_kind, const void* pool, int64_t n_pool, int64_t ld_pool,
+                            const int64_t* idx, int64_t n, int k, int d, double scale, void* P, int blend, double w,
+                            const double* w_dev, void* A, void* B, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5  dictionary update (one block-coordinate-descent sweep)
@@ -284,6 +319,7 @@ typedef struct {
   onmf_lars_stats* stats;                 /* or NULL */
   void* main_stream;
   void* side_stream;
+  double* w_dev;                          /* one device double (blend weight of onmf_step_graph) or NULL */
 } onmf_step_buffers;
 
 /* timing_slots > 0: the plan keeps a ring of event pairs around the coder launch (read with onmf_step_plan_lars_ms) */
@@ -300,6 +336,12 @@ int onmf_step_launch(onmf_step_plan* plan, const onmf_step_buffers* b, const voi
 int onmf_step_finish(onmf_step_plan* plan, const onmf_step_buffers* b, double w, int cur);
 int onmf_step(onmf_step_plan* plan, const onmf_step_buffers* b, const void* Xt, const void* codes, int64_t n, double w,
               int cur);
+/* onmf_step as ONE CUDA graph launch (single GPU; b->w_dev must be set).  The graph of a given (Xt, codes, n, cur,
+ * buffers) is captured the second time that key is seen and replayed afterwards; anything a graph cannot express
+ * (track_C, timing slots, hold_coder) and first sights fall through to onmf_step.  Same results, bit for bit. */
+int onmf_step_graph(onmf_step_plan* plan, const onmf_step_buffers* b, const void* Xt, const void* codes, int64_t n, double w,
+                    int cur);
+long long onmf_step_plan_graph_steps(const onmf_step_plan* plan);   /* steps that ran as a graph replay */
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,8 @@ SIGNATURES = {
     "onmf_gather_patches": (_i, [_i, _vp, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp]),
     "onmf_gather_rows": (_i, [_i, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "onmf_transpose": (_i, [_i, _i, _vp, _i64, _i64, _vp, _vp]),
+    "onmf_convert": (_i, [_i, _i, _vp, _i64, _vp, _vp]),
+    "onmf_widen": (_i, [_i, _vp, _i64, _dbl, _vp, _vp, _vp]),
     "onmf_gram": (_i, [_i, _vp, _i, _i, _vp, _vp]),
     "onmf_gram_workspace": (_sz, [_i, _i, _i]),
     "onmf_gram_ws": (_i, [_i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
@@ -54,6 +56,7 @@ SIGNATURES = {
     "onmf_surrogate_workspace": (_sz, [_i, _i64, _i, _i]),
     "onmf_surrogate_partial": (_i, [_i, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _vp]),
     "onmf_surrogate_blend": (_i, [_i, _vp, _i, _i, _dbl, _vp, _vp, _vp]),
+    "onmf_surrogate_blend_dev": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "onmf_xxt_partial": (_i, [_i, _vp, _i64, _i, _vp, _vp, _sz, _vp]),
     "onmf_axpby": (_i, [_i, _i64, _dbl, _vp, _dbl, _vp, _vp]),
     "onmf_tc_supported": (_i, [_i, _i]),
@@ -62,6 +65,10 @@ SIGNATURES = {
     "onmf_cov_tc": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp, _vp]),
     "onmf_surrogate_tc_workspace": (_sz, [_i64, _i, _i]),
     "onmf_surrogate_partial_tc": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _vp]),
+    "onmf_fused_tc_supported": (_i, [_i, _i]),
+    "onmf_cov_fused_tc": (_i, [_i, _vp, _i64, _i64, _vp, _i64, _i, _dbl, _vp, _vp, _i, _vp, _vp]),
+    "onmf_surrogate_fused_tc_workspace": (_sz, [_i64, _i, _i]),
+    "onmf_surrogate_fused_tc": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _i64, _i, _i, _dbl, _vp, _i, _dbl, _vp, _vp, _vp, _vp, _sz, _vp]),
     "onmf_update_dict": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "onmf_update_dict_workspace": (_sz, [_i, _i, _i]),
     "onmf_update_dict_ws": (_i, [_i, _vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
@@ -81,6 +88,8 @@ SIGNATURES = {
     "onmf_step_launch": (_i, [_vp, _vp, _vp, _vp, _i64, _i]),
     "onmf_step_finish": (_i, [_vp, _vp, _dbl, _i]),
     "onmf_step": (_i, [_vp, _vp, _vp, _vp, _i64, _dbl, _i]),
+    "onmf_step_graph": (_i, [_vp, _vp, _vp, _vp, _i64, _dbl, _i]),
+    "onmf_step_plan_graph_steps": (ctypes.c_longlong, [_vp]),
 }
 
 
@@ -93,7 +102,8 @@ class StepBuffers(ctypes.Structure):
                 ("A", _vp), ("B", _vp), ("C", _vp), ("P", _vp * 2), ("P2", _vp),
                 ("Ct", _vp), ("Ht", _vp), ("Xhi", _vp), ("Xlo", _vp), ("Hhi", _vp), ("Hlo", _vp),
                 ("ws_lars", _vp), ("ws_lars_bytes", _sz), ("ws_sur", _vp), ("ws_sur_bytes", _sz),
-                ("ws_gram", _vp), ("ws_gram_bytes", _sz), ("stats", _vp), ("main_stream", _vp), ("side_stream", _vp)]
+                ("ws_gram", _vp), ("ws_gram_bytes", _sz), ("stats", _vp), ("main_stream", _vp), ("side_stream", _vp),
+                ("w_dev", _vp)]
 
 
 _lib = None
@@ -175,6 +185,31 @@ def transpose(src, out, stream=None):
     rows, cols = src.shape
     _check(load().onmf_transpose(dt(src), dt(out), _ptr(src), rows, cols, _ptr(out), _stream(stream)), "onmf_transpose")
     return out
+
+
+STORE_U8, STORE_F16 = 2, 3
+
+
+def convert(src, dst, stream=None):
+    """elementwise f32 <-> f64"""
+    _req(src, "src"); _req(dst, "dst")
+    _check(load().onmf_convert(dt(src), dt(dst), _ptr(src), src.numel(), _ptr(dst), _stream(stream)), "onmf_convert")
+    return dst
+
+
+def widen(src, scale, dst, lo=None, stream=None):
+    """dst (float32) = float(src) * scale for a uint8 / float16 device tensor; with lo: the TF32 (hi, lo) pair."""
+    _req(src, "src"); _req(dst, "dst", torch.float32)
+    if lo is not None:
+        _req(lo, "lo", torch.float32)
+    if src.dtype == torch.uint8:
+        kind = STORE_U8
+    elif src.dtype == torch.float16:
+        kind = STORE_F16
+    else:
+        raise OnmfKernelError("widen: source must be uint8 or float16")
+    _check(load().onmf_widen(kind, _ptr(src), src.numel(), float(scale), _ptr(dst), _ptr(lo), _stream(stream)), "onmf_widen")
+    return dst
 
 
 OPT_LARS_RESERVED_SMS = 1
@@ -368,6 +403,61 @@ def surrogate_partial_tc(Hhi, Hlo, Xhi, Xlo, P, workspace, stream=None):
     return P
 
 
+# ---- fused tensor-core path (csrc/gemm_fused.cu): minibatch read once, as stored ---------------------
+
+def fused_tc_supported(k, d):
+    return bool(load().onmf_fused_tc_supported(int(k), int(d)))
+
+
+def _store_kind(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.uint8:
+        return STORE_U8
+    if t.dtype == torch.float16:
+        return STORE_F16
+    raise OnmfKernelError("minibatch storage must be float32, uint8 or float16 (got %s)" % t.dtype)
+
+
+def cov_fused_tc(pool, idx, n, Whi, Wlo, Ct, scale=1.0, stream=None):
+    """Ct (n x k) = pool[idx] @ W; pool (n_pool x d) float32 / uint8 / float16, idx int64 (n) or None (rows 0..n-1)."""
+    _req(pool, "pool"); _req(Whi, "Whi", torch.float32); _req(Wlo, "Wlo", torch.float32); _req(Ct, "Ct", torch.float32)
+    if idx is not None:
+        _req(idx, "idx", torch.int64)
+    d, k = Whi.shape
+    _check(load().onmf_cov_fused_tc(_store_kind(pool), _ptr(pool), pool.shape[0], pool.stride(0), _ptr(idx), int(n), d,
+                                    float(scale), _ptr(Whi), _ptr(Wlo), k, _ptr(Ct), _stream(stream)), "onmf_cov_fused_tc")
+    return Ct
+
+
+def surrogate_fused_tc_workspace(n, k, d):
+    return int(load().onmf_surrogate_fused_tc_workspace(int(n), int(k), int(d)))
+
+
+def surrogate_fused_tc(Ht, pool, idx, n, d, P, workspace, scale=1.0, blend=None, stream=None):
+    """P (k x (k+d)) = [Ht^T Ht | Ht^T pool[idx]]; blend = (w or a device float64 tensor, A, B) also applies the A/B recursion."""
+    _req(Ht, "Ht", torch.float32); _req(pool, "pool"); _req(workspace, "workspace", torch.uint8)
+    if P is not None:
+        _req(P, "P", torch.float32)
+    if idx is not None:
+        _req(idx, "idx", torch.int64)
+    k = Ht.shape[1]
+    w, w_dev, A, B = 0.0, None, None, None
+    if blend is not None:
+        wv, A, B = blend
+        _req(A, "A", torch.float32); _req(B, "B", torch.float32)
+        if isinstance(wv, torch.Tensor):
+            _req(wv, "w_dev", torch.float64)
+            w_dev = wv
+        else:
+            w = float(wv)
+    _check(load().onmf_surrogate_fused_tc(_ptr(Ht), _store_kind(pool), _ptr(pool), pool.shape[0], pool.stride(0), _ptr(idx), int(n),
+                                          k, int(d), float(scale), _ptr(P), 1 if blend is not None else 0, w, _ptr(w_dev),
+                                          _ptr(A), _ptr(B), _ptr(workspace), workspace.numel(), _stream(stream)),
+           "onmf_surrogate_fused_tc")
+    return P
+
+
 # ---- batched reconstruction ---------------------------------------------------------------------
 
 def pgd_code_columns(G, Ct, alpha, sub_iter, stopping_diff, Ht, stream=None):
@@ -447,3 +537,10 @@ class StepPlan:
 
     def step(self, bufs, Xt, codes, n, w, cur):
         _check(load().onmf_step(self._h, ctypes.byref(bufs), _ptr(Xt), _ptr(codes), int(n), float(w), int(cur)), "onmf_step")
+
+    def step_graph(self, bufs, Xt, codes, n, w, cur):
+        _check(load().onmf_step_graph(self._h, ctypes.byref(bufs), _ptr(Xt), _ptr(codes), int(n), float(w), int(cur)),
+               "onmf_step_graph")
+
+    def graph_steps(self):
+        return int(load().onmf_step_plan_graph_steps(self._h))

@@ -75,22 +75,25 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
       if (has_row) bnext = B[(size_t)(j + 1) * d + row0 + rl];
     }
     if (j + 2 < k) issue_col(j + 2);
-    T acc0 = T(0), acc1 = T(0);
+    // W A[:,j] and B[j,:] are O(A_jj) while their difference is the O(1e-2 .. 1e-4) update: accumulated in the working
+    // precision the cancellation amplifies fp32 rounding ~1e4x (5.7e-3 per atom after 10 steps at d=1024, k=256).  The
+    // products of fp32 numbers are exact in FP64, so the dot product and the difference are formed in FP64 in both modes.
+    double acc0 = 0.0, acc1 = 0.0;
     if (has_row) {
       int q = tl;
       for (; q + tpr < k; q += 2 * tpr) {
-        acc0 += wrow[q] * a[q];
-        acc1 += wrow[q + tpr] * a[q + tpr];
+        acc0 += (double)wrow[q] * (double)a[q];
+        acc1 += (double)wrow[q + tpr] * (double)a[q + tpr];
       }
-      if (q < k) acc0 += wrow[q] * a[q];
+      if (q < k) acc0 += (double)wrow[q] * (double)a[q];
     }
-    T dot = acc0 + acc1;
+    double dot = acc0 + acc1;
     for (int off = tpr >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
     T wnew = T(0);
     if (has_row) {
-      const T c = T(1) / (a[j] + T(1));
-      wnew = wrow[j] - c * (dot - bcur);
-      wnew = wnew > T(0) ? wnew : T(0);
+      const double c = 1.0 / ((double)a[j] + 1.0);
+      const double v = (double)wrow[j] - c * (dot - (double)bcur);
+      wnew = v > 0.0 ? (T)v : T(0);
     }
     bcur = bnext;
     T sq = (has_row && tl == 0) ? wnew * wnew : T(0);
@@ -146,16 +149,16 @@ __global__ void __launch_bounds__(256) bcd_global_kernel(const T* __restrict__ W
     const int par = j & 1;
     for (int q = tid; q < k; q += blockDim.x) aj[q] = A[(size_t)q * k + j];
     __syncthreads();
-    const T c = T(1) / (aj[j] + T(1));
+    const double c = 1.0 / ((double)aj[j] + 1.0);
     T sq = T(0);
     for (int r = warp; r < nrows; r += nwarp) {        // one warp per row, rows of a warp in increasing order
       const T* wrow = Wout + (size_t)(row0 + r) * k;
-      T dot = T(0);
-      for (int q = lane; q < k; q += 32) dot += wrow[q] * aj[q];
+      double dot = 0.0;                                  // FP64 accumulation: see bcd_kernel
+      for (int q = lane; q < k; q += 32) dot += (double)wrow[q] * (double)aj[q];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-      T v = wrow[j] - c * (dot - B[(size_t)j * d + row0 + r]);
-      v = v > T(0) ? v : T(0);
+      const double vd = (double)wrow[j] - (double)c * (dot - (double)B[(size_t)j * d + row0 + r]);
+      const T v = vd > 0.0 ? (T)vd : T(0);
       if (lane == 0) { wn[r] = v; sq += v * v; }
     }
     if (lane == 0) warp_part[warp] = sq;

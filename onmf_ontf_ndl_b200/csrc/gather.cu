@@ -499,3 +499,66 @@ extern "C" int onmf_edge_scatter_add(int dtype, const void* R, int64_t ldr, cons
   ONMF_LAUNCH_CHECK("edge_scatter_kernel");
   return ONMF_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Narrow STORAGE formats for streamed minibatches (arithmetic stays fp32): image data is 8-bit before the reference divides
+// it by 255 (image_reconstruction.py:88 `data = np.asarray(img) / 255`), so a host-resident stream of patches can cross PCIe
+// as u8 (or fp16) -- 4x (2x) fewer bytes than fp32 -- and be widened on the device.  dst = (float)src * scale, optionally
+// written directly as the TF32 hi/lo pair of the tensor-core path (hi = rna_tf32(x), lo = x - hi).
+// ------------------------------------------------------------------------------------------------
+#include <cuda_fp16.h>
+namespace onmf {
+template <typename S> __device__ __forceinline__ float widen(S v);
+template <> __device__ __forceinline__ float widen<unsigned char>(unsigned char v) { return (float)v; }
+template <> __device__ __forceinline__ float widen<__half>(__half v) { return __half2float(v); }
+
+template <typename S, bool SPLIT>
+__global__ void widen_kernel(const S* __restrict__ src, long long count, float scale, float* __restrict__ dst, float* __restrict__ lo) {
+  // 4 elements per thread per iteration (count % 4 == 0; src 4-element aligned): one 4- or 8-byte load, float4 stores
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < count / 4; i += stride) {
+    S v[4];
+    if (sizeof(S) == 1) *reinterpret_cast<uint32_t*>(v) = reinterpret_cast<const uint32_t*>(src)[i];
+    else *reinterpret_cast<uint2*>(v) = reinterpret_cast<const uint2*>(src)[i];
+    float x[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x[e] = widen<S>(v[e]) * scale;
+    if (SPLIT) {
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x[e]));
+        h[e] = __uint_as_float(t);
+        l[e] = x[e] - h[e];
+      }
+      reinterpret_cast<float4*>(dst)[i] = make_float4(h[0], h[1], h[2], h[3]);
+      reinterpret_cast<float4*>(lo)[i] = make_float4(l[0], l[1], l[2], l[3]);
+    } else {
+      reinterpret_cast<float4*>(dst)[i] = make_float4(x[0], x[1], x[2], x[3]);
+    }
+  }
+}
+}  // namespace onmf
+
+extern "C" int onmf_widen(int src_kind, const void* src, int64_t count, double scale, void* dst, void* lo, void* stream) {
+  if (!src || !dst || count < 0 || count % 4) return fail(ONMF_E_ARG, "widen: bad argument (count must be a multiple of 4)");
+  if (src_kind != ONMF_STORE_U8 && src_kind != ONMF_STORE_F16) return fail(ONMF_E_ARG, "widen: src_kind must be ONMF_STORE_U8 or ONMF_STORE_F16");
+  if ((reinterpret_cast<uintptr_t>(src) & 7) || (reinterpret_cast<uintptr_t>(dst) & 15) || (lo && (reinterpret_cast<uintptr_t>(lo) & 15)))
+    return fail(ONMF_E_ARG, "widen: pointers must be aligned (src 8 B, dst/lo 16 B)");
+  if (count == 0) return ONMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = (int)cdiv<long long>(count / 4, 256);
+  if (grid > 16 * num_sms()) grid = 16 * num_sms();
+  const float sc = (float)scale;
+  if (src_kind == ONMF_STORE_U8) {
+    if (lo) widen_kernel<unsigned char, true><<<grid, 256, 0, st>>>((const unsigned char*)src, count, sc, (float*)dst, (float*)lo);
+    else widen_kernel<unsigned char, false><<<grid, 256, 0, st>>>((const unsigned char*)src, count, sc, (float*)dst, nullptr);
+  } else {
+    if (lo) widen_kernel<__half, true><<<grid, 256, 0, st>>>((const __half*)src, count, sc, (float*)dst, (float*)lo);
+    else widen_kernel<__half, false><<<grid, 256, 0, st>>>((const __half*)src, count, sc, (float*)dst, nullptr);
+  }
+  ONMF_LAUNCH_CHECK("widen_kernel");
+  return ONMF_OK;
+}

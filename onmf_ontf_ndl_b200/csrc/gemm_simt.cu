@@ -124,6 +124,26 @@ __global__ void blend_kernel(const T* __restrict__ P, int k, int d, T w, T* __re
   }
 }
 
+// same, blend weight read from device memory (the CUDA-graph form of the step: w = t^-beta changes every replay)
+template <typename T>
+__global__ void blend_dev_kernel(const T* __restrict__ P, int k, int d, const double* __restrict__ w_dev, T* __restrict__ A,
+                                 T* __restrict__ B) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long tot = (long long)k * (k + d);
+  if (i >= tot) return;
+  const T w = (T)(*w_dev);
+  int r = (int)(i / (k + d)), c = (int)(i - (long long)r * (k + d));
+  T p = P[i];
+  T om = T(1) - w;
+  if (c < k) {
+    size_t o = (size_t)r * k + c;
+    A[o] = om * A[o] + w * p;
+  } else {
+    size_t o = (size_t)r * d + (c - k);
+    B[o] = om * B[o] + w * p;
+  }
+}
+
 template <typename T>
 __global__ void axpby_kernel(long long count, T a, const T* __restrict__ x, T b, T* __restrict__ y) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -441,6 +461,39 @@ extern "C" int onmf_surrogate_blend(int dtype, const void* P, int k, int d, doub
   else if (dtype == ONMF_F64) blend_kernel<double><<<grid, 256, 0, st>>>((const double*)P, k, d, w, (double*)A, (double*)B);
   else return fail(ONMF_E_ARG, "surrogate_blend: bad dtype");
   ONMF_LAUNCH_CHECK("blend_kernel");
+  return ONMF_OK;
+}
+
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ src, long long count, TO* __restrict__ dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < count; i += stride) dst[i] = (TO)src[i];
+}
+
+extern "C" int onmf_convert(int dtype_in, int dtype_out, const void* src, int64_t count, void* dst, void* stream) {
+  if (!src || !dst || count < 0) return fail(ONMF_E_ARG, "convert: bad argument");
+  if (count == 0) return ONMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = (int)cdiv<long long>(count, 256);
+  if (grid > 16 * num_sms()) grid = 16 * num_sms();
+  if (dtype_in == ONMF_F32 && dtype_out == ONMF_F64) convert_kernel<float, double><<<grid, 256, 0, st>>>((const float*)src, count, (double*)dst);
+  else if (dtype_in == ONMF_F64 && dtype_out == ONMF_F32) convert_kernel<double, float><<<grid, 256, 0, st>>>((const double*)src, count, (float*)dst);
+  else return fail(ONMF_E_ARG, "convert: f32 <-> f64 only");
+  ONMF_LAUNCH_CHECK("convert_kernel");
+  return ONMF_OK;
+}
+
+extern "C" int onmf_surrogate_blend_dev(int dtype, const void* P, int k, int d, const double* w_dev, void* A, void* B,
+                                        void* stream) {
+  if (!P || !A || !B || !w_dev || k <= 0 || d <= 0) return fail(ONMF_E_ARG, "surrogate_blend_dev: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long tot = (long long)k * (k + d);
+  unsigned grid = (unsigned)cdiv<long long>(tot, 256);
+  if (dtype == ONMF_F32) blend_dev_kernel<float><<<grid, 256, 0, st>>>((const float*)P, k, d, w_dev, (float*)A, (float*)B);
+  else if (dtype == ONMF_F64) blend_dev_kernel<double><<<grid, 256, 0, st>>>((const double*)P, k, d, w_dev, (double*)A, (double*)B);
+  else return fail(ONMF_E_ARG, "surrogate_blend_dev: bad dtype");
+  ONMF_LAUNCH_CHECK("blend_dev_kernel");
   return ONMF_OK;
 }
 

@@ -472,6 +472,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
     // at the previous knot, which matters when the path stops inside the segment that ended with the drop.
     int ghost_atom = -1;
     T ghost_prev = T(0), ghost_val = T(0);
+    int banned = -1;                     // fp32: atom dropped by the most recent drop step (see the arg-max)
 
     while (!__all_sync(0xffffffffu, done)) {
       __syncwarp();
@@ -487,6 +488,30 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         for (int m = NA - 1; m >= 0; --m)
           if (cov[m] == best) bi = atom_of(m);
         bi = __reduce_min_sync(gmask, bi);
+        // fp32 only: the atom dropped by the last drop step can never be the joiner of the first join knot after it -- in
+        // exact arithmetic its covariance has fallen strictly below the active level by then (it left because its
+        // correlation decays faster than the level).  When the drop and the next join are a near-tie (the step between
+        // them shorter than one ulp of the covariances) its recomputed covariance can round to the level or one ulp above,
+        // it wins the arg-max, re-enters with coefficient 0 and the path derails (one column's code off by 30 %, enough to
+        // move the dictionary by 1e-3: tests/test_gpu_parity.py::test_cfg5_full_run_fp32_bars).  sklearn's float64 loop
+        // has the same hazard at 1e-16 instead of 1e-7; the fp64 coder stays literal.
+        const bool use_ban = (banned >= 0) && !drop && !done;
+        if (__any_sync(0xffffffffu, use_ban && bi == banned)) {
+          T b2 = -Num<T>::inf();
+          int i2 = 0x7fffffff;
+#pragma unroll
+          for (int m = 0; m < NA; ++m) {
+            const T cv = (use_ban && atom_of(m) == banned) ? -Num<T>::inf() : cov[m];
+            b2 = cv > b2 ? cv : b2;
+          }
+          b2 = gmaxval<LPC>(b2, gmask);
+#pragma unroll
+          for (int m = NA - 1; m >= 0; --m)
+            if (cov[m] == b2 && !(use_ban && atom_of(m) == banned)) i2 = atom_of(m);
+          i2 = __reduce_min_sync(gmask, i2);
+          if (use_ban && bi == banned && b2 > -Num<T>::inf()) { best = b2; bi = i2; }   // (no other candidate: keep it)
+        }
+        if (!drop) banned = -1;
       } else {
 #pragma unroll
         for (int m = 0; m < NA; ++m) {
@@ -671,7 +696,8 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
 #pragma unroll
       for (int m = 0; m < NA; ++m) {
         const T den = AA - corr[m] + tiny;
-        T v = qdiv(C - cov[m], den);
+        // (fp32: an inactive covariance one ulp above C -- the just-dropped atom excluded from the arg-max -- is a tie)
+        T v = qdiv((sizeof(T) == 4) ? (C - cov[m] > T(0) ? C - cov[m] : T(0)) : (C - cov[m]), den);
         // sklearn's min_pos takes strictly positive candidates.  C is the maximum, so the numerator is >= 0 and
         // v > 0 <=> den > 0 unless the atom TIES with the joining one (numerator exactly 0), where sklearn steps past
         // it.  In fp64 that is a structural (measure-zero) event and is reproduced literally; in fp32 a near-tie
@@ -740,7 +766,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
         wp0 = gsum<LPC>(wp0);
         rp0 = gsum<LPC>(rp0);
         mpp = gsum<LPC>(mpp);
-        if (dodrop) { ghost_atom = a_d; ghost_prev = gp; }
+        if (dodrop) { ghost_atom = a_d; ghost_prev = gp; banned = a_d; }
         __syncwarp();
         sweep_u(mv, us, sD, dodrop ? n_act : 0, dodrop);
         double sum_m = 0.0;
@@ -1012,7 +1038,8 @@ constexpr int HYB_SLOTS = 64, HYB_SPLIT = LARS_HYB_SPLIT;
 static size_t ws_hyb_bytes(int kp) {
   if (kp <= 128) return 0;
   size_t per = (size_t)(HYB_SLOTS * (HYB_SLOTS + 1) / 2 - HYB_SPLIT * (HYB_SPLIT + 1) / 2) * sizeof(double);
-  return round_up<size_t>((size_t)(num_sms() > 160 ? num_sms() : 160) * (LARS_MAX_THREADS / 32) * per, 256);
+  // resident groups per SM: one per LPC lanes; the k > 128 classes use LPC >= 16
+  return round_up<size_t>((size_t)(num_sms() > 160 ? num_sms() : 160) * (LARS_MAX_THREADS / 16) * per, 256);
 }
 
 // tiers: S0 slots, then S1, S2, S3 (0 = none); the last non-zero tier keeps M in global scratch when GL
@@ -1093,7 +1120,11 @@ static int lasso_lars_t(const void* G, const double* G64, const void* Ct, long l
     case 0: return launch_class<T, 8, 4, 32, 0, 0, 0, false>(g, G64, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
     case 1: return launch_class<T, 16, 4, 32, 64, 0, 0, false>(g, G64, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
     case 2: return launch_class<T, 32, 4, 32, 64, 128, 0, false>(g, G64, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+#if defined(LARS_K256_LPC16)
+    case 3: return launch_class<T, 16, 16, HYB_SLOTS, 128, 256, 0, true, HYB_SPLIT>(g, G64, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+#else
     case 3: return launch_class<T, 32, 8, HYB_SLOTS, 128, 256, 0, true, HYB_SPLIT>(g, G64, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
+#endif
     case 4: return launch_class<T, 32, 16, HYB_SLOTS, 128, 512, 0, true, HYB_SPLIT>(g, G64, c, n, k, d, alpha, max_iter, h, w, stats, first_tier, st);
   }
   return fail(ONMF_E_UNSUPPORTED, "lasso_lars: n_components > 512 not instantiated");

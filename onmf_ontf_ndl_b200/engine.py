@@ -25,11 +25,15 @@ import torch
 from . import _lib
 
 
+RAW_NORM = 1.5      # a dictionary with a column norm beyond this counts as raw (unnormalised): see OnmfEngine.set_state
+
+
 class OnmfEngine:
     def __init__(self, d: int, k: int, alpha: float = 1.0, beta: Optional[float] = None,
                  dtype: torch.dtype = torch.float32, device=None, max_iter: int = 1000,
                  process_group=None, track_C: bool = False, collect_stats: bool = False, use_tc=None,
-                 reserve_sms: Optional[int] = None, fused: bool = True, lars_timing: bool = False):
+                 reserve_sms: Optional[int] = None, fused: bool = True, lars_timing: bool = False,
+                 graph: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise _lib.OnmfKernelError("OnmfEngine needs a CUDA device (there is no CPU path)")
         _lib.load()
@@ -99,6 +103,11 @@ class OnmfEngine:
         self._plan = _lib.StepPlan(timing_slots=256 if lars_timing else 0) if self.fused else None
         self._pairs = None
         self._sb = None
+        # CUDA-graph replay of the fused step (single GPU): default on; ONMF_B200_GRAPH=0 disables
+        if graph is None:
+            graph = os.environ.get("ONMF_B200_GRAPH", "1") != "0"
+        self.graph = bool(graph) and self.fused and self.world == 1
+        self._w_dev = torch.zeros(1, dtype=torch.float64, device=dev)
 
     @property
     def launches(self):
@@ -137,6 +146,7 @@ class OnmfEngine:
         sb.ws_gram = p(self._ws_gram); sb.ws_gram_bytes = self._ws_gram.numel()
         sb.stats = p(self.stats)
         sb.main_stream, sb.side_stream = self.main.cuda_stream, self.side.cuda_stream
+        sb.w_dev = p(self._w_dev)
         self._sb = sb
 
     def reset_lars_timing(self):
@@ -159,6 +169,18 @@ class OnmfEngine:
             else:
                 dst.copy_(torch.as_tensor(src).to(self.device, self.dtype))
         self._derive(self.W, self.G, getattr(self, "Whi", None), getattr(self, "Wlo", None), self.main)
+        # A raw initial dictionary (the reference's W0 = np.random.rand(d, r), src/ontf.py:213, columns of norm ~sqrt(d/3))
+        # makes the covariances O(d/4) while the path is decided by differences of O(1e-5): beyond fp32 resolution.  The
+        # dictionary update puts every column into the unit ball, so only the FIRST minibatch after set_state is coded
+        # against such a dictionary; the fp32 engine codes that one minibatch with the FP64 coder (see _code_wide).
+        self._raw_W = False
+        if self.dtype == torch.float32:
+            Wn = W if isinstance(W, torch.Tensor) else None
+            if Wn is None:
+                import numpy as _np
+                self._raw_W = bool(_np.max(_np.linalg.norm(_np.asarray(W, dtype=_np.float64), axis=0)) > RAW_NORM)
+            else:
+                self._raw_W = bool(float(torch.diagonal(self.G).max().item()) > RAW_NORM ** 2)
         # the first dictionary update (side stream) reads W, A, B and shares the Gram workspace with the derive above
         if self._plan is not None:
             self._plan.mark_state(self.main)
@@ -221,9 +243,11 @@ class OnmfEngine:
     def sparse_code(self, Xt: torch.Tensor, W: Optional[torch.Tensor] = None, alpha=None, out=None):
         """Ht (n x k) = positive lasso_lars codes of the rows of Xt (n x d) against W (default: current)."""
         n = Xt.shape[0]
-        self._reserve(n)
+        self._reserve(max(n, 1))
         Ct = self.Ct[:n]
         Ht = self.Ht[:n] if out is None else out
+        if n == 0:
+            return Ht
         if W is None:
             self.flush()
             W, G = self.W, self.G
@@ -239,10 +263,30 @@ class OnmfEngine:
         else:
             _lib.cov(Xt, W, Ct)
             self.launches += 1
-        _lib.lasso_lars(G, Ct, self.d, self.alpha if alpha is None else alpha, Ht, self._ws_lars,
-                        max_iter=self.max_iter, stats=self._stats_ptr())
-        self.launches += self._lars_launches()
+        a = self.alpha if alpha is None else alpha
+        wide = self.dtype == torch.float32 and (self._raw_W if G is self.G else
+                                                float(torch.diagonal(G).max().item()) > RAW_NORM ** 2)
+        if wide:
+            self._lars_wide(G, Ct, a, Ht, torch.cuda.current_stream(self.device))
+        else:
+            _lib.lasso_lars(G, Ct, self.d, a, Ht, self._ws_lars, max_iter=self.max_iter, stats=self._stats_ptr())
+            self.launches += self._lars_launches()
         return Ht
+
+    def _lars_wide(self, G64, Ct, alpha, Ht, stream):
+        """fp32 engine, raw dictionary: the coder in FP64 on the fp32 covariances (FP64 Gram as always), codes rounded to
+        fp32.  Temporary FP64 copies of Ct / Ht live only for this call."""
+        n = Ct.shape[0]
+        with torch.cuda.stream(stream):
+            Ct64 = torch.empty(n, self.k, dtype=torch.float64, device=self.device)
+            Ht64 = torch.empty(n, self.k, dtype=torch.float64, device=self.device)
+            ws = torch.zeros(_lib.lasso_lars_workspace(torch.float64, self.k, n), dtype=torch.uint8, device=self.device)
+            _lib.convert(Ct, Ct64, stream=stream)
+            _lib.lasso_lars(G64, Ct64, self.d, alpha, Ht64, ws, max_iter=self.max_iter, stats=self._stats_ptr(), stream=stream)
+            _lib.convert(Ht64, Ht, stream=stream)
+            for t_ in (Ct64, Ht64, ws):
+                t_.record_stream(stream)
+        self.launches += 2 + self._lars_launches()
 
     # ------------------------------------------------------------------ one online step
     def step_with_codes(self, Xt, Ht, t):
@@ -267,6 +311,25 @@ class OnmfEngine:
         self._reserve(max(n, 1))
         w = float(t) ** (-self.beta)
         cur = self._cur
+        if self._raw_W and codes is None:
+            # first minibatch against a raw initial dictionary (fp32 engine): code it with the FP64 coder, then run the
+            # normal step on those codes (aggregation + dictionary update are unaffected)
+            self._raw_W = os.environ.get("ONMF_B200_WIDE_ALWAYS") == "1"      # (analysis switch: FP64 coder at every step)
+            if n > 0:
+                main_ = self.main
+                Ct, Ht = self.Ct[:n], self.Ht[:n]
+                if self.use_tc:
+                    if not presplit:
+                        _lib.split_tf32(Xt, self.Xhi[:n], self.Xlo[:n], stream=main_)
+                        self.launches += 1
+                    _lib.cov_tc(self.Xhi[:n], self.Xlo[:n], self.Whi, self.Wlo, Ct, stream=main_)
+                else:
+                    _lib.cov(Xt, self.W, Ct, stream=main_)
+                self.launches += 1
+                self._lars_wide(self.G, Ct, self.alpha, Ht, main_)
+                codes = Ht
+        if os.environ.get("ONMF_B200_WIDE_ALWAYS") != "1":
+            self._raw_W = False
         if self.fused:
             return self._step_fused(Xt, codes, n, w, cur)
         # side stream: dictionary update for this step with the OLD aggregates (src/ontf.py:151).  It is
@@ -377,6 +440,8 @@ class OnmfEngine:
                 if self.track_C:
                     dist.all_reduce(self.P2, group=self.pg)
             self._plan.finish(self._sb, w, cur)
+        elif self.graph:
+            self._plan.step_graph(self._sb, Xt, codes, n, w, cur)
         else:
             self._plan.step(self._sb, Xt, codes, n, w, cur)
         self.W, self.W_next = self.W_next, self.W
@@ -388,22 +453,34 @@ class OnmfEngine:
         return self.Ht[:n] if codes is None else codes
 
     # ------------------------------------------------------------------ host-buffer entry (end-to-end path)
-    def step_host(self, Xt_host: torch.Tensor, t: float, W_out_host: Optional[torch.Tensor] = None):
+    def step_host(self, Xt_host: torch.Tensor, t: float, W_out_host: Optional[torch.Tensor] = None, scale: Optional[float] = None):
         """step() for a minibatch that lives in (pinned) HOST memory, sample-major (n x d).
 
-        The host->device copy runs on a copy stream into one of two staging buffers, so the copy of
-        minibatch t+1 overlaps the coding of minibatch t; if W_out_host (pinned, d x k) is given the updated
-        dictionary is copied back asynchronously after the step's dictionary update.  Nothing blocks the host;
-        call flush()+synchronize (or read_back()) before touching W_out_host."""
+        Xt_host may be float32 / float64 (the engine's dtype), or a narrower STORAGE format -- uint8 (scale defaults to
+        1/255, the reference's `data / 255`, image_reconstruction.py:88) or float16 (scale 1) -- which crosses PCIe at a
+        quarter / half of the bytes and is widened to fp32 on the device (onmf_widen, fused with the TF32 hi/lo split on
+        the tensor-core path); arithmetic is fp32 either way.
+
+        The host->device copy runs on a copy stream into one of two staging buffers, so the copy of minibatch t+1 overlaps
+        the coding of minibatch t; if W_out_host (pinned, d x k) is given the updated dictionary is copied back
+        asynchronously after the step's dictionary update.  Nothing blocks the host; call flush()+synchronize (or
+        read_back()) before touching W_out_host."""
         if Xt_host.is_cuda:
             raise _lib.OnmfKernelError("step_host expects a host tensor")
         n = Xt_host.shape[0]
-        if not hasattr(self, "_stage") or self._stage[0].shape[0] < n:
-            self._stage = [torch.empty(max(n, 1), self.d, dtype=self.dtype, device=self.device) for _ in range(2)]
+        sdt = Xt_host.dtype
+        narrow = sdt in (torch.uint8, torch.float16)
+        if not narrow and sdt != self.dtype:
+            raise _lib.OnmfKernelError("step_host: minibatch dtype %s (engine %s; uint8 / float16 storage also accepted)" % (sdt, self.dtype))
+        if narrow and (self.dtype != torch.float32 or (n * self.d) % 4):
+            raise _lib.OnmfKernelError("step_host: uint8 / float16 storage needs the fp32 engine and n*d % 4 == 0")
+        if not hasattr(self, "_stage") or self._stage[0].shape[0] < n or self._stage[0].dtype != sdt:
+            self._stage = [torch.empty(max(n, 1), self.d, dtype=sdt, device=self.device) for _ in range(2)]
             self._stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
             self._stage_i = 0
             self._copy = torch.cuda.Stream(self.device)
             self._ev_h2d = torch.cuda.Event()
+            self._wide = None
         i = self._stage_i
         self._stage_i ^= 1
         buf = self._stage[i][:n]
@@ -412,8 +489,26 @@ class OnmfEngine:
             buf.copy_(Xt_host, non_blocking=True)
             self._ev_h2d.record(self._copy)
         self.main.wait_event(self._ev_h2d)
-        Ht = self.step(buf, t)
-        self._stage_ev[i].record(self.main)
+        if narrow:
+            sc = (1.0 / 255.0 if sdt == torch.uint8 else 1.0) if scale is None else float(scale)
+            if self.use_tc:
+                hi, lo = self.split_buffers(n)
+                if n:
+                    _lib.widen(buf, sc, hi, lo, stream=self.main)
+                    self.launches += 1
+                self._stage_ev[i].record(self.main)        # the staging buffer is free as soon as it has been widened
+                Ht = self.step(None, t, n=n)
+            else:
+                if self._wide is None or self._wide.shape[0] < n:
+                    self._wide = torch.empty(max(n, 1), self.d, dtype=torch.float32, device=self.device)
+                if n:
+                    _lib.widen(buf, sc, self._wide[:n], stream=self.main)
+                    self.launches += 1
+                self._stage_ev[i].record(self.main)
+                Ht = self.step(self._wide[:n], t)
+        else:
+            Ht = self.step(buf, t)
+            self._stage_ev[i].record(self.main)
         if W_out_host is not None:
             with torch.cuda.stream(self.side):
                 W_out_host.copy_(self.W, non_blocking=True)     # self.W is the dictionary this step produced

@@ -104,6 +104,8 @@ def reconstruct_network(G, W, embs, alpha=0, precision=None):
     n, kk = embs.shape
     if kk * kk != d:
         raise ValueError("dictionary has %d rows, expected k^2 = %d" % (d, kk * kk))
+    if n == 0:
+        return np.empty((0, 2), dtype=object), np.empty(0), np.empty(0, dtype=np.int64)
     rowptr, colidx, nodes = patches.graph_to_csr(G)
     pos = {u: i for i, u in enumerate(nodes)}
     emb_i = np.asarray([[pos[u] for u in row] for row in embs.tolist()], dtype=np.int32).reshape(n, kk)

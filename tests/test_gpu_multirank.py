@@ -70,7 +70,7 @@ def test_class_api_two_ranks_gloo_one_device(golden_dir):
     """Online_NTF.train_dict_single / Online_NMF.train_dict with torch.distributed initialised (two gloo ranks sharing
     cuda:0): rank 0's draws are broadcast, minibatches shard by columns, every rank returns the golden single-process
     result and bit-identical dictionaries."""
-    import tests._mr_class_worker as wk
+    import _mr_class_worker as wk
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mgr = mp.Manager()
     out = mgr.dict()
