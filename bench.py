@@ -239,7 +239,6 @@ def run_ours(args):
     eng = OnmfEngine(d, k, alpha=alpha, dtype=dt, device=dev, process_group=pg, collect_stats=True, fused=not args.timeline,
                      lars_timing=not graph_mode, graph=graph_mode)
     eng.set_state(W0)
-    Xb = None if eng.use_tc else torch.empty(n, d, dtype=dt, device=dev)
     main = eng.main
 
     def barrier():
@@ -247,15 +246,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    idx_buf = [torch.empty(n, dtype=torch.int64, device=dev) for _ in range(2)]
+
     def one_step(t, eng=eng):
-        idx = torch.randint(0, n, (n,), device=dev, generator=gen)     # fresh minibatch: resample the pool (with replacement)
-        if eng.use_tc:
-            hi, lo = eng.split_buffers(n)
-            _lib.gather_rows_split(pool, idx, hi, lo)                   # K1 fused with the TF32 hi/lo split
-            eng.step(None, float(t), n=n)
-        else:
-            _lib.gather_rows(pool, idx, Xb)
-            eng.step(Xb, float(t))
+        # fresh minibatch: resample the pool (with replacement); the step takes the minibatch BY REFERENCE (pool + indices):
+        # on the fused tensor-core path K1 (gather) happens inside the covariance / partial-sum kernels, otherwise the
+        # engine runs the K1 gather kernel first
+        idx = idx_buf[t & 1]
+        torch.randint(0, n, (n,), device=dev, generator=gen, out=idx)
+        eng.step_pool(pool, idx, float(t))
 
     t = 0
     for _ in range(Wm):
@@ -334,7 +333,7 @@ def run_ours(args):
                 sys.stderr.write("  %-10s %8.3f %8.3f\n" % (lab, t0_, t1_))
     clocks = sampler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
-    launches = (eng.launches - launches0) + K          # + the gather kernel per step
+    launches = eng.launches - launches0
     stats = eng.read_stats()
     graph_steps = eng._plan.graph_steps() if eng._plan is not None else 0
     if graph_mode:
@@ -395,7 +394,7 @@ def run_ours(args):
     # the reference's drivers hold before `data / 255`, image_reconstruction.py:88): a quarter of the PCIe bytes, widened to
     # fp32 on the device (onmf_widen fused with the TF32 split); arithmetic unchanged.  Reported beside the fp32 line.
     e2e_u8 = None
-    if (n * d) % 4 == 0:
+    if d % 4 == 0:
         del host
         g8 = torch.Generator(); g8.manual_seed(99 + rank)
         host8 = [torch.randint(0, 256, (n, d), dtype=torch.uint8, generator=g8).pin_memory() for _ in range(2)]

@@ -322,6 +322,18 @@ typedef struct {
   double* w_dev;                          /* one device double (blend weight of onmf_step_graph) or NULL */
 } onmf_step_buffers;
 
+/* A minibatch by reference (fused tensor-core path, onmf_fused_tc_supported): rows idx[0..n) of a stored sample-major pool
+ * in fp32 or a narrow storage format -- X_batch = X_unfold[:, idx] (src/ontf.py:231) without materialising it. */
+typedef struct {
+  int kind;              /* ONMF_F32, ONMF_STORE_U8 or ONMF_STORE_F16 */
+  const void* base;      /* pool, one sample per row */
+  int64_t n_pool;        /* rows in the pool */
+  int64_t ld;            /* row pitch in elements */
+  const int64_t* idx;    /* n row indices, or NULL for rows 0..n-1 */
+  int64_t n;             /* minibatch size (this rank's columns) */
+  double scale;          /* value = stored * scale (1/255 for 8-bit image data, image_reconstruction.py:88) */
+} onmf_minibatch;
+
 /* timing_slots > 0: the plan keeps a ring of event pairs around the coder launch (read with onmf_step_plan_lars_ms) */
 int onmf_step_plan_create(onmf_step_plan** plan, int timing_slots);
 int onmf_step_plan_destroy(onmf_step_plan* plan);
@@ -342,6 +354,15 @@ int onmf_step(onmf_step_plan* plan, const onmf_step_buffers* b, const void* Xt, 
 int onmf_step_graph(onmf_step_plan* plan, const onmf_step_buffers* b, const void* Xt, const void* codes, int64_t n, double w,
                     int cur);
 long long onmf_step_plan_graph_steps(const onmf_step_plan* plan);   /* steps that ran as a graph replay */
+/* the same four entry points for a minibatch passed by reference: cov and the partial sums read the pool rows in place
+ * (gemm_fused.cu), and on a single GPU (onmf_step_mb / onmf_step_graph_mb) the blend is fused into the partial-sum
+ * reduction.  ONMF_E_UNSUPPORTED unless use_tc, fp32 and onmf_fused_tc_supported(k, d); ws_sur must then hold
+ * onmf_surrogate_fused_tc_workspace(n, k, d) bytes. */
+int onmf_step_launch_mb(onmf_step_plan* plan, const onmf_step_buffers* b, const onmf_minibatch* mb, const void* codes, int cur);
+int onmf_step_mb(onmf_step_plan* plan, const onmf_step_buffers* b, const onmf_minibatch* mb, const void* codes, double w,
+                 int cur);
+int onmf_step_graph_mb(onmf_step_plan* plan, const onmf_step_buffers* b, const onmf_minibatch* mb, const void* codes, double w,
+                       int cur);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,9 @@ SIGNATURES = {
     "onmf_step": (_i, [_vp, _vp, _vp, _vp, _i64, _dbl, _i]),
     "onmf_step_graph": (_i, [_vp, _vp, _vp, _vp, _i64, _dbl, _i]),
     "onmf_step_plan_graph_steps": (ctypes.c_longlong, [_vp]),
+    "onmf_step_launch_mb": (_i, [_vp, _vp, _vp, _vp, _i]),
+    "onmf_step_mb": (_i, [_vp, _vp, _vp, _vp, _dbl, _i]),
+    "onmf_step_graph_mb": (_i, [_vp, _vp, _vp, _vp, _dbl, _i]),
 }
 
 
@@ -104,6 +107,25 @@ class StepBuffers(ctypes.Structure):
                 ("ws_lars", _vp), ("ws_lars_bytes", _sz), ("ws_sur", _vp), ("ws_sur_bytes", _sz),
                 ("ws_gram", _vp), ("ws_gram_bytes", _sz), ("stats", _vp), ("main_stream", _vp), ("side_stream", _vp),
                 ("w_dev", _vp)]
+
+
+class Minibatch(ctypes.Structure):
+    """onmf_minibatch (include/onmf_b200.h): a minibatch by reference -- rows idx[0..n) of a stored pool."""
+    _fields_ = [("kind", _i), ("base", _vp), ("n_pool", _i64), ("ld", _i64), ("idx", _vp), ("n", _i64), ("scale", _dbl)]
+
+
+def make_minibatch(pool, idx, n, scale=1.0):
+    _req(pool, "pool")
+    if idx is not None:
+        _req(idx, "idx", torch.int64)
+    mb = Minibatch()
+    mb.kind = _store_kind(pool)
+    mb.base = pool.data_ptr()
+    mb.n_pool, mb.ld = pool.shape[0], pool.stride(0)
+    mb.idx = idx.data_ptr() if idx is not None else None
+    mb.n = int(n)
+    mb.scale = float(scale)
+    return mb
 
 
 _lib = None
@@ -544,3 +566,10 @@ class StepPlan:
 
     def graph_steps(self):
         return int(load().onmf_step_plan_graph_steps(self._h))
+
+    def launch_mb(self, bufs, mb, codes, cur):
+        _check(load().onmf_step_launch_mb(self._h, ctypes.byref(bufs), ctypes.byref(mb), _ptr(codes), int(cur)), "onmf_step_launch_mb")
+
+    def step_mb(self, bufs, mb, codes, w, cur, graph=False):
+        fn = load().onmf_step_graph_mb if graph else load().onmf_step_mb
+        _check(fn(self._h, ctypes.byref(bufs), ctypes.byref(mb), _ptr(codes), float(w), int(cur)), "onmf_step_mb")

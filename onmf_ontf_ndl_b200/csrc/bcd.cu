@@ -67,28 +67,40 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
   if (k > 1) issue_col(1);
   T bcur = has_row ? B[(size_t)0 * d + row0 + rl] : T(0);
 
+  // W A[:,j] and B[j,:] are O(A_jj) while their difference is the O(1e-2 .. 1e-4) update: accumulated in the working
+  // precision the cancellation amplifies fp32 rounding ~1e4x.  The products of fp32 numbers are exact in FP64, so the dot
+  // product and the difference are formed in FP64 in both modes.
+  // team dot product of this row with column `a` of A, leaving out index `skip` (-1: none)
+  auto team_dot = [&](const T* a, int skip) -> double {
+    double acc0 = 0.0, acc1 = 0.0;
+    if (has_row) {
+      int q = tl;
+      for (; q + tpr < k; q += 2 * tpr) {
+        if (q != skip) acc0 += (double)wrow[q] * (double)a[q];
+        if (q + tpr != skip) acc1 += (double)wrow[q + tpr] * (double)a[q + tpr];
+      }
+      if (q < k && q != skip) acc0 += (double)wrow[q] * (double)a[q];
+    }
+    double dsum = acc0 + acc1;
+    for (int off = tpr >> 1; off > 0; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
+    return dsum;
+  };
+  double dot = team_dot(aj, -1);                 // atom 0: nothing pending
+
+  // Software pipeline over atoms.  Column j of W is final only after the cluster-wide norm of its new entries; column
+  // j+1's dot product needs it in ONE term (W[row, j] A[j, j+1]).  So the norm reduction of atom j (DSMEM pushes + one
+  // split-phase barrier.cluster) is in flight while every team already forms the rest of atom j+1's dot product; the
+  // scaled term is added after the barrier.  Column j+1 of A (strided, L2 resident) and B[j+1, row] are requested one
+  // full atom step before they are consumed.
   for (int j = 0; j < k; ++j) {
     const int par = j & 1;
     const T* a = aj + par * k;
+    const T* an = aj + (par ^ 1) * k;
     if (j + 1 < k) {
       store_col(j + 1, aj + (par ^ 1) * k);       // requested during the previous step; nobody reads this buffer now
       if (has_row) bnext = B[(size_t)(j + 1) * d + row0 + rl];
     }
     if (j + 2 < k) issue_col(j + 2);
-    // W A[:,j] and B[j,:] are O(A_jj) while their difference is the O(1e-2 .. 1e-4) update: accumulated in the working
-    // precision the cancellation amplifies fp32 rounding ~1e4x (5.7e-3 per atom after 10 steps at d=1024, k=256).  The
-    // products of fp32 numbers are exact in FP64, so the dot product and the difference are formed in FP64 in both modes.
-    double acc0 = 0.0, acc1 = 0.0;
-    if (has_row) {
-      int q = tl;
-      for (; q + tpr < k; q += 2 * tpr) {
-        acc0 += (double)wrow[q] * (double)a[q];
-        acc1 += (double)wrow[q + tpr] * (double)a[q + tpr];
-      }
-      if (q < k) acc0 += (double)wrow[q] * (double)a[q];
-    }
-    double dot = acc0 + acc1;
-    for (int off = tpr >> 1; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
     T wnew = T(0);
     if (has_row) {
       const double c = 1.0 / ((double)a[j] + 1.0);
@@ -100,7 +112,7 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
     if ((tid & 31) == 0) warp_part[tid >> 5] = sq;
-    __syncthreads();
+    __syncthreads();                               // (also: column j+1 of A is now visible to every team)
     if (tid < 32) {
       T v = (tid < (nthr + 31) / 32) ? warp_part[tid] : T(0);
 #pragma unroll
@@ -110,12 +122,18 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
         peer[par * BCD_MAX_CLUSTER + rank] = v;
       }
     }
-    cluster.sync();
+    cluster.barrier_arrive();                      // release: the pushes above are visible to whoever passes the wait
+    // ---- in the shadow of the reduction: atom j+1's dot product without its j-th term ----
+    double pdot = 0.0;
+    if (j + 1 < k) pdot = team_dot(an, j);
+    cluster.barrier_wait();
     T tot = T(0);
     for (int r = 0; r < csize; ++r) tot += slots[par * BCD_MAX_CLUSTER + r];
     const T nrm = sqrt(tot);
     const T sc = T(1) / (nrm > T(1) ? nrm : T(1));
-    if (has_row && tl == 0) Ws[(size_t)rl * ks + j] = sc * wnew;
+    const T wfin = sc * wnew;
+    if (has_row && tl == 0) Ws[(size_t)rl * ks + j] = wfin;
+    if (j + 1 < k) dot = pdot + (has_row ? (double)wfin * (double)an[j] : 0.0);
     __syncwarp();
   }
   __syncthreads();

@@ -10,13 +10,20 @@
 //   main : [split X] -> cov(W[cur]) -> [wait(AB_{t-1}) if hold_coder] -> LARS -> [split H] -> partial sums -> record(P_t, code_t)
 //   side : wait(P_t) -> (all-reduce by the caller) -> blend -> record(AB_t)
 //   main : wait(W_t)                                       -- the next coding needs the new dictionary only
+//
+// The minibatch comes either as a dense sample-major matrix Xt (n x d) or -- tensor-core path, k <= 256 -- as a DESCRIPTOR
+// (onmf_minibatch: stored pool + row indices + storage format): then the fused kernels of gemm_fused.cu read the pool rows
+// in place (gather, widening and TF32 split inside the loaders), nothing of the minibatch is ever copied or split in HBM,
+// and on a single GPU the blend is the epilogue of the partial-sum reduction:
+//   main : cov_fused(pool, idx) -> LARS -> wait(W_t) -> sur_fused(Ht, pool, idx) + reduce + blend -> record(code_t, AB_t)
 #include <new>
 
 #include "common.cuh"
 
 // one instantiated CUDA graph of the whole step for a fixed (minibatch pointer, codes pointer, n, cur, buffers)
 struct StepGraph {
-  const void* Xt;
+  const void* Xt;             // minibatch base pointer (Xt, or the pool of a minibatch descriptor)
+  const void* idx;            // minibatch row indices (descriptor form) or nullptr
   const void* codes;
   long long n;
   int cur;
@@ -135,51 +142,82 @@ static int check_buffers(const onmf_step_buffers* b, bool need_code_bufs) {
   return ONMF_OK;
 }
 
-extern "C" int onmf_step_launch(onmf_step_plan* p, const onmf_step_buffers* b, const void* Xt, const void* codes,
-                                int64_t n, int cur) {
-  if (!p) return fail(ONMF_E_ARG, "step_launch: null plan");
-  int rc = check_buffers(b, n > 0);
-  if (rc) return rc;
-  if (n < 0 || (cur != 0 && cur != 1)) return fail(ONMF_E_ARG, "step_launch: bad argument");
-  const bool presplit = (Xt == nullptr);
-  if (n > 0 && presplit && !b->use_tc) return fail(ONMF_E_ARG, "step_launch: Xt = NULL needs the tensor-core path");
-  if (n > 0 && presplit && b->track_C) return fail(ONMF_E_ARG, "step_launch: track_C needs the unsplit minibatch");
-  cudaStream_t main = (cudaStream_t)b->main_stream, side = (cudaStream_t)b->side_stream;
+// what one step consumes: a dense minibatch or a descriptor (exactly one of Xt / mb, or neither on the pre-split path)
+struct StepIn {
+  const void* Xt;              // dense (n x d) in the engine dtype, or nullptr
+  const onmf_minibatch* mb;    // descriptor (fused tensor-core path), or nullptr
+  const void* codes;           // externally computed codes (n x k) or nullptr
+  long long n;
+};
+
+// blend request of a step: none (the caller blends after its all-reduce), host weight, or device weight (graph replay)
+struct Blend {
+  int mode;                    // 0 none, 1 host w, 2 *w_dev
+  double w;
+};
+
+static bool mb_fused(const onmf_step_buffers* b, const StepIn& in) {
+  return in.mb != nullptr && b->use_tc && onmf_fused_tc_supported(b->k, b->d);
+}
+
+// Enqueue one step.  captured = false: two streams ordered by the plan's events (cross-step overlap);
+// captured = true: fork/join on p->cap + side for stream capture (no event recorded outside the capture is waited on).
+// On return *blended says whether A, B already hold the blended aggregates (fused epilogue) or P[cur] awaits blending.
+static int enqueue_step(onmf_step_plan* p, const onmf_step_buffers* b, const StepIn& in, int cur, const Blend& bl, bool captured,
+                        bool* blended, long long* kernels) {
+  cudaStream_t main = captured ? p->cap : (cudaStream_t)b->main_stream, side = (cudaStream_t)b->side_stream;
   const int dt = b->dtype, d = b->d, k = b->k, nx = cur ^ 1;
   const size_t esz = dt == ONMF_F64 ? 8 : 4;
+  const long long n = in.n;
+  const bool fused = mb_fused(b, in);
+  const bool presplit = (in.Xt == nullptr && in.mb == nullptr);
+  int rc;
+  long long kn = 0;
+  *blended = false;
 
   // ---- side: dictionary update with the OLD aggregates, then everything the coder derives from the dictionary ----
-  ONMF_CUDA(cudaStreamWaitEvent(side, p->ev_code, 0));
+  if (captured) {
+    ONMF_CUDA(cudaEventRecord(p->ev_g0, main));
+    ONMF_CUDA(cudaStreamWaitEvent(side, p->ev_g0, 0));                    // fork
+  } else {
+    ONMF_CUDA(cudaStreamWaitEvent(side, p->ev_code, 0));
+  }
   // (the large-dictionary fallback of the update borrows the Gram workspace: same stream, used one after the other)
   if ((rc = onmf_update_dict_ws(dt, b->W[cur], b->A, b->B, d, k, b->W[nx], b->ws_gram, b->ws_gram_bytes, side))) return rc;
   if ((rc = onmf_gram_f64(dt, b->W[nx], d, k, b->G[nx], nullptr, b->ws_gram, b->ws_gram_bytes, side))) return rc;
-  p->launches += 3;
+  kn += 3;
   if (b->use_tc) {
     if ((rc = onmf_split_tf32(b->W[nx], b->Whi[nx], b->Wlo[nx], (int64_t)d * k, side))) return rc;
-    p->launches += 1;
+    kn += 1;
   }
-  ONMF_CUDA(cudaEventRecord(p->ev_W, side));
+  ONMF_CUDA(cudaEventRecord(captured ? p->ev_g2 : p->ev_W, side));
 
   // ---- main: code this minibatch with W[cur], partial sums ----
-  if (b->track_C) ONMF_CUDA(cudaStreamWaitEvent(main, p->ev_AB, 0));     // P2 is single-buffered (AB is recorded after C's blend)
+  if (b->track_C && !captured) ONMF_CUDA(cudaStreamWaitEvent(main, p->ev_AB, 0));   // P2 is single-buffered (AB is recorded after C's blend)
+  // the blend may ride on the partial-sum reduction when this call owns the whole step (single GPU) on the fused path
+  const bool fuse_blend = fused && bl.mode != 0 && !b->track_C;
   if (n > 0) {
-    const void* Hcodes = codes ? codes : b->Ht;
-    if (b->use_tc && !presplit) {
-      if ((rc = onmf_split_tf32(Xt, b->Xhi, b->Xlo, n * d, main))) return rc;
-      p->launches += 1;
+    const void* Hcodes = in.codes ? in.codes : b->Ht;
+    if (b->use_tc && !fused && !presplit) {
+      if ((rc = onmf_split_tf32(in.Xt, b->Xhi, b->Xlo, n * d, main))) return rc;
+      kn += 1;
     }
-    if (!codes) {
-      if (!b->Ct || !b->ws_lars) return fail(ONMF_E_ARG, "step_launch: null coder buffer");
-      if (b->use_tc) rc = onmf_cov_tc(b->Xhi, b->Xlo, n, d, b->Whi[cur], b->Wlo[cur], k, b->Ct, main);
-      else rc = onmf_cov(dt, Xt, n, d, b->W[cur], k, b->Ct, main);
+    if (!in.codes) {
+      if (!b->Ct || !b->ws_lars) return fail(ONMF_E_ARG, "step: null coder buffer");
+      if (fused)
+        rc = onmf_cov_fused_tc(in.mb->kind, in.mb->base, in.mb->n_pool, in.mb->ld, in.mb->idx, n, d, in.mb->scale, b->Whi[cur],
+                               b->Wlo[cur], k, b->Ct, main);
+      else if (b->use_tc) rc = onmf_cov_tc(b->Xhi, b->Xlo, n, d, b->Whi[cur], b->Wlo[cur], k, b->Ct, main);
+      else rc = onmf_cov(dt, in.Xt, n, d, b->W[cur], k, b->Ct, main);
       if (rc) return rc;
       // the dictionary update is one thread-block cluster: it is only placed while a group of SMs in one GPC is free,
       // i.e. before the persistent coder has spread over the GPU -- hold the coder until the blend it follows is done
-      if (b->hold_coder) ONMF_CUDA(cudaStreamWaitEvent(main, p->ev_AB, 0));
-      int rsv = b->reserve_sms >= 0 ? b->reserve_sms : ((long long)n * k <= 131072LL * 256 ? 8 : 0);
+      if (b->hold_coder && !captured) ONMF_CUDA(cudaStreamWaitEvent(main, p->ev_AB, 0));
+      const int rsv = b->reserve_sms >= 0 ? b->reserve_sms : 0;
       const int saved = g_lars_reserved_sms;
       g_lars_reserved_sms = rsv;
-      if (p->tslots > 0) ONMF_CUDA(cudaEventRecord(p->t0[p->tcount % p->tslots], main));
+      const bool timed = p->tslots > 0 && !captured;
+      if (timed) ONMF_CUDA(cudaEventRecord(p->t0[p->tcount % p->tslots], main));
       if (dt == ONMF_F32)
         rc = onmf_lasso_lars_g64(dt, b->G[cur], b->Ct, n, k, d, b->alpha, b->max_iter, b->Ht, b->ws_lars, b->ws_lars_bytes,
                                  b->stats, -1, main);
@@ -188,29 +226,69 @@ extern "C" int onmf_step_launch(onmf_step_plan* p, const onmf_step_buffers* b, c
                                 b->stats, -1, main);
       g_lars_reserved_sms = saved;
       if (rc) return rc;
-      if (p->tslots > 0) {
+      if (timed) {
         ONMF_CUDA(cudaEventRecord(p->t1[p->tcount % p->tslots], main));
         ++p->tcount;
       }
-      p->launches += 1 + lars_launch_count(k);
+      kn += 1 + lars_launch_count(k);
     }
-    if (b->use_tc) {
+    if (fused) {
+      if (fuse_blend) {
+        // the blend overwrites A, B: the dictionary update (side) must have finished reading them
+        ONMF_CUDA(cudaStreamWaitEvent(main, captured ? p->ev_g2 : p->ev_W, 0));
+        rc = onmf_surrogate_fused_tc(Hcodes, in.mb->kind, in.mb->base, in.mb->n_pool, in.mb->ld, in.mb->idx, n, k, d, in.mb->scale,
+                                     nullptr, 1, bl.w, bl.mode == 2 ? b->w_dev : nullptr, b->A, b->B, b->ws_sur, b->ws_sur_bytes, main);
+        *blended = true;
+      } else {
+        rc = onmf_surrogate_fused_tc(Hcodes, in.mb->kind, in.mb->base, in.mb->n_pool, in.mb->ld, in.mb->idx, n, k, d, in.mb->scale,
+                                     b->P[cur], 0, 0.0, nullptr, nullptr, nullptr, b->ws_sur, b->ws_sur_bytes, main);
+      }
+      if (rc) return rc;
+      kn += 2;
+    } else if (b->use_tc) {
       if ((rc = onmf_split_tf32(Hcodes, b->Hhi, b->Hlo, n * k, main))) return rc;
       if ((rc = onmf_surrogate_partial_tc(b->Hhi, b->Hlo, b->Xhi, b->Xlo, n, k, d, b->P[cur], b->ws_sur, b->ws_sur_bytes, main)))
         return rc;
-      p->launches += 5;
+      kn += 5;
     } else {
-      if ((rc = onmf_surrogate_partial(dt, Hcodes, Xt, n, k, d, b->P[cur], b->ws_sur, b->ws_sur_bytes, main))) return rc;
-      p->launches += 3;
+      if ((rc = onmf_surrogate_partial(dt, Hcodes, in.Xt, n, k, d, b->P[cur], b->ws_sur, b->ws_sur_bytes, main))) return rc;
+      kn += 3;
     }
     if (b->track_C) {
-      if ((rc = onmf_xxt_partial(dt, Xt, n, d, b->P2, b->ws_sur, b->ws_sur_bytes, main))) return rc;
-      p->launches += 2;
+      if ((rc = onmf_xxt_partial(dt, in.Xt, n, d, b->P2, b->ws_sur, b->ws_sur_bytes, main))) return rc;
+      kn += 2;
     }
   } else {
     ONMF_CUDA(cudaMemsetAsync(b->P[cur], 0, (size_t)k * (k + d) * esz, main));
     if (b->track_C) ONMF_CUDA(cudaMemsetAsync(b->P2, 0, (size_t)d * d * esz, main));
   }
+  *kernels = kn;
+  return ONMF_OK;
+}
+
+static int check_step_in(const onmf_step_buffers* b, const StepIn& in, int cur, const char* who) {
+  int rc = check_buffers(b, in.n > 0);
+  if (rc) return rc;
+  if (in.n < 0 || (cur != 0 && cur != 1)) return fail(ONMF_E_ARG, who);
+  if (in.Xt && in.mb) return fail(ONMF_E_ARG, "step: pass either a dense minibatch or a descriptor, not both");
+  if (in.mb) {
+    if (in.mb->n != in.n) return fail(ONMF_E_ARG, "step: descriptor row count differs from n");
+    if (!mb_fused(b, in)) return fail(ONMF_E_UNSUPPORTED, "step: a minibatch descriptor needs the fused tensor-core path (fp32, onmf_fused_tc_supported)");
+    if (b->track_C) return fail(ONMF_E_UNSUPPORTED, "step: track_C needs a dense minibatch");
+  }
+  const bool presplit = (in.Xt == nullptr && in.mb == nullptr);
+  if (in.n > 0 && presplit && !b->use_tc) return fail(ONMF_E_ARG, "step: Xt = NULL needs the tensor-core path");
+  if (in.n > 0 && presplit && b->track_C) return fail(ONMF_E_ARG, "step: track_C needs the unsplit minibatch");
+  return ONMF_OK;
+}
+
+// ---- stream schedule -------------------------------------------------------------------------------------------------
+static int launch_streams(onmf_step_plan* p, const onmf_step_buffers* b, const StepIn& in, int cur, const Blend& bl, bool* blended) {
+  cudaStream_t main = (cudaStream_t)b->main_stream, side = (cudaStream_t)b->side_stream;
+  long long kn = 0;
+  int rc = enqueue_step(p, b, in, cur, bl, false, blended, &kn);
+  if (rc) return rc;
+  p->launches += kn;
   ONMF_CUDA(cudaEventRecord(p->ev_P, main));
   ONMF_CUDA(cudaEventRecord(p->ev_code, main));
   // ---- side: the blend (and the caller's all-reduce before it) needs this step's partial sums ----
@@ -218,27 +296,71 @@ extern "C" int onmf_step_launch(onmf_step_plan* p, const onmf_step_buffers* b, c
   return ONMF_OK;
 }
 
-extern "C" int onmf_step_finish(onmf_step_plan* p, const onmf_step_buffers* b, double w, int cur) {
-  if (!p) return fail(ONMF_E_ARG, "step_finish: null plan");
-  int rc = check_buffers(b, false);
-  if (rc) return rc;
+static int finish_streams(onmf_step_plan* p, const onmf_step_buffers* b, double w, int cur, bool blended) {
   cudaStream_t main = (cudaStream_t)b->main_stream, side = (cudaStream_t)b->side_stream;
-  if ((rc = onmf_surrogate_blend(b->dtype, b->P[cur], b->k, b->d, w, b->A, b->B, side))) return rc;
-  p->launches += 1;
+  int rc;
+  if (!blended) {
+    if ((rc = onmf_surrogate_blend(b->dtype, b->P[cur], b->k, b->d, w, b->A, b->B, side))) return rc;
+    p->launches += 1;
+  }
   if (b->track_C) {
     if ((rc = onmf_axpby(b->dtype, (int64_t)b->d * b->d, w, b->P2, 1.0 - w, b->C, side))) return rc;
     p->launches += 1;
   }
-  ONMF_CUDA(cudaEventRecord(p->ev_AB, side));
-  ONMF_CUDA(cudaStreamWaitEvent(main, p->ev_W, 0));     // the next coding needs the new dictionary only
+  ONMF_CUDA(cudaEventRecord(p->ev_AB, side));        // (blended on main: side has waited for ev_P, recorded after that blend)
+  ONMF_CUDA(cudaStreamWaitEvent(main, p->ev_W, 0));  // the next coding needs the new dictionary only
   return ONMF_OK;
+}
+
+extern "C" int onmf_step_launch(onmf_step_plan* p, const onmf_step_buffers* b, const void* Xt, const void* codes,
+                                int64_t n, int cur) {
+  if (!p) return fail(ONMF_E_ARG, "step_launch: null plan");
+  StepIn in{Xt, nullptr, codes, n};
+  int rc = check_step_in(b, in, cur, "step_launch: bad argument");
+  if (rc) return rc;
+  bool blended;
+  return launch_streams(p, b, in, cur, Blend{0, 0.0}, &blended);
+}
+
+extern "C" int onmf_step_launch_mb(onmf_step_plan* p, const onmf_step_buffers* b, const onmf_minibatch* mb, const void* codes, int cur) {
+  if (!p || !mb) return fail(ONMF_E_ARG, "step_launch_mb: null plan / descriptor");
+  StepIn in{nullptr, mb, codes, mb->n};
+  int rc = check_step_in(b, in, cur, "step_launch_mb: bad argument");
+  if (rc) return rc;
+  bool blended;
+  return launch_streams(p, b, in, cur, Blend{0, 0.0}, &blended);
+}
+
+extern "C" int onmf_step_finish(onmf_step_plan* p, const onmf_step_buffers* b, double w, int cur) {
+  if (!p) return fail(ONMF_E_ARG, "step_finish: null plan");
+  int rc = check_buffers(b, false);
+  if (rc) return rc;
+  return finish_streams(p, b, w, cur, false);
+}
+
+static int step_streams(onmf_step_plan* p, const onmf_step_buffers* b, const StepIn& in, double w, int cur) {
+  bool blended = false;
+  int rc = launch_streams(p, b, in, cur, Blend{1, w}, &blended);
+  if (rc) return rc;
+  return finish_streams(p, b, w, cur, blended);
 }
 
 extern "C" int onmf_step(onmf_step_plan* p, const onmf_step_buffers* b, const void* Xt, const void* codes, int64_t n,
                          double w, int cur) {
-  int rc = onmf_step_launch(p, b, Xt, codes, n, cur);
+  if (!p) return fail(ONMF_E_ARG, "step: null plan");
+  StepIn in{Xt, nullptr, codes, n};
+  int rc = check_step_in(b, in, cur, "step: bad argument");
   if (rc) return rc;
-  return onmf_step_finish(p, b, w, cur);
+  return step_streams(p, b, in, w, cur);
+}
+
+extern "C" int onmf_step_mb(onmf_step_plan* p, const onmf_step_buffers* b, const onmf_minibatch* mb, const void* codes, double w,
+                            int cur) {
+  if (!p || !mb) return fail(ONMF_E_ARG, "step_mb: null plan / descriptor");
+  StepIn in{nullptr, mb, codes, mb->n};
+  int rc = check_step_in(b, in, cur, "step_mb: bad argument");
+  if (rc) return rc;
+  return step_streams(p, b, in, w, cur);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -248,115 +370,68 @@ extern "C" int onmf_step(onmf_step_plan* p, const onmf_step_buffers* b, const vo
 // stream.  For the small configurations (BASELINE configs[0..3]: a step is ~15 dependent launches of a few microseconds
 // each) this removes the per-launch CPU cost and the inter-kernel gaps.  The blend weight w = t^-beta changes every
 // step: it is read from device memory (buffers->w_dev), refreshed by a stream-ordered 8-byte copy before each launch.
-// Graphs are cached per (minibatch pointer, codes pointer, n, cur, buffer descriptor); a key is captured the second
+// Graphs are cached per (minibatch pointers, codes pointer, n, cur, buffer descriptor); a key is captured the second
 // time it is seen, so one-off calls never pay for capture + instantiation.
 // ------------------------------------------------------------------------------------------------------------------
-static unsigned long long buffers_sig(const onmf_step_buffers* b) {
+static unsigned long long buffers_sig(const onmf_step_buffers* b, const onmf_minibatch* mb) {
   unsigned long long h = 1469598103934665603ULL;
   const unsigned char* q = reinterpret_cast<const unsigned char*>(b);
   for (size_t i = 0; i < sizeof(*b); ++i) { h ^= q[i]; h *= 1099511628211ULL; }
+  if (mb) {
+    const unsigned long long v[4] = {(unsigned long long)mb->kind, (unsigned long long)mb->n_pool, (unsigned long long)mb->ld, 0ull};
+    double sc = mb->scale;
+    unsigned long long scb;
+    memcpy(&scb, &sc, 8);
+    for (int i = 0; i < 3; ++i) { h ^= v[i]; h *= 1099511628211ULL; }
+    h ^= scb; h *= 1099511628211ULL;
+  }
   return h;
 }
 
-static int enqueue_captured(onmf_step_plan* p, const onmf_step_buffers* b, const void* Xt, const void* codes, int64_t n, int cur,
-                            long long* kernels) {
-  // the main branch is captured on the plan's own stream (kernels do not care which stream recorded them; the graph is
-  // launched on the caller's main stream afterwards)
-  cudaStream_t main = p->cap, side = (cudaStream_t)b->side_stream;
-  const int dt = b->dtype, d = b->d, k = b->k, nx = cur ^ 1;
-  const size_t esz = dt == ONMF_F64 ? 8 : 4;
-  const bool presplit = (Xt == nullptr);
-  int rc;
-  long long kn = 0;
-  ONMF_CUDA(cudaEventRecord(p->ev_g0, main));
-  ONMF_CUDA(cudaStreamWaitEvent(side, p->ev_g0, 0));                      // fork
-  if ((rc = onmf_update_dict_ws(dt, b->W[cur], b->A, b->B, d, k, b->W[nx], b->ws_gram, b->ws_gram_bytes, side))) return rc;
-  if ((rc = onmf_gram_f64(dt, b->W[nx], d, k, b->G[nx], nullptr, b->ws_gram, b->ws_gram_bytes, side))) return rc;
-  kn += 3;
-  if (b->use_tc) {
-    if ((rc = onmf_split_tf32(b->W[nx], b->Whi[nx], b->Wlo[nx], (int64_t)d * k, side))) return rc;
-    kn += 1;
-  }
-  if (n > 0) {
-    const void* Hcodes = codes ? codes : b->Ht;
-    if (b->use_tc && !presplit) {
-      if ((rc = onmf_split_tf32(Xt, b->Xhi, b->Xlo, n * d, main))) return rc;
-      kn += 1;
-    }
-    if (!codes) {
-      if (!b->Ct || !b->ws_lars) return fail(ONMF_E_ARG, "step_graph: null coder buffer");
-      if (b->use_tc) rc = onmf_cov_tc(b->Xhi, b->Xlo, n, d, b->Whi[cur], b->Wlo[cur], k, b->Ct, main);
-      else rc = onmf_cov(dt, Xt, n, d, b->W[cur], k, b->Ct, main);
-      if (rc) return rc;
-      const int saved = g_lars_reserved_sms;
-      g_lars_reserved_sms = b->reserve_sms >= 0 ? b->reserve_sms : 0;
-      if (dt == ONMF_F32)
-        rc = onmf_lasso_lars_g64(dt, b->G[cur], b->Ct, n, k, d, b->alpha, b->max_iter, b->Ht, b->ws_lars, b->ws_lars_bytes,
-                                 b->stats, -1, main);
-      else
-        rc = onmf_lasso_lars_ex(dt, b->G[cur], b->Ct, n, k, d, b->alpha, b->max_iter, b->Ht, b->ws_lars, b->ws_lars_bytes,
-                                b->stats, -1, main);
-      g_lars_reserved_sms = saved;
-      if (rc) return rc;
-      kn += 1 + lars_launch_count(k);
-    }
-    if (b->use_tc) {
-      if ((rc = onmf_split_tf32(Hcodes, b->Hhi, b->Hlo, n * k, main))) return rc;
-      if ((rc = onmf_surrogate_partial_tc(b->Hhi, b->Hlo, b->Xhi, b->Xlo, n, k, d, b->P[cur], b->ws_sur, b->ws_sur_bytes, main)))
-        return rc;
-      kn += 5;
-    } else {
-      if ((rc = onmf_surrogate_partial(dt, Hcodes, Xt, n, k, d, b->P[cur], b->ws_sur, b->ws_sur_bytes, main))) return rc;
-      kn += 3;
-    }
-  } else {
-    ONMF_CUDA(cudaMemsetAsync(b->P[cur], 0, (size_t)k * (k + d) * esz, main));
-  }
-  ONMF_CUDA(cudaEventRecord(p->ev_g1, main));
-  ONMF_CUDA(cudaStreamWaitEvent(side, p->ev_g1, 0));
-  if ((rc = onmf_surrogate_blend_dev(dt, b->P[cur], k, d, b->w_dev, b->A, b->B, side))) return rc;
-  kn += 1;
-  ONMF_CUDA(cudaEventRecord(p->ev_g2, side));
-  ONMF_CUDA(cudaStreamWaitEvent(main, p->ev_g2, 0));                      // join
-  *kernels = kn;
-  return ONMF_OK;
-}
-
-extern "C" int onmf_step_graph(onmf_step_plan* p, const onmf_step_buffers* b, const void* Xt, const void* codes, int64_t n,
-                               double w, int cur) {
-  if (!p) return fail(ONMF_E_ARG, "step_graph: null plan");
-  int rc = check_buffers(b, n > 0);
-  if (rc) return rc;
-  if (n < 0 || (cur != 0 && cur != 1)) return fail(ONMF_E_ARG, "step_graph: bad argument");
-  const bool presplit = (Xt == nullptr);
-  if (n > 0 && presplit && !b->use_tc) return fail(ONMF_E_ARG, "step_graph: Xt = NULL needs the tensor-core path");
+static int step_graph_impl(onmf_step_plan* p, const onmf_step_buffers* b, const StepIn& in, double w, int cur) {
   // not expressible as this graph: the d x d aggregate (host-side w in its blend), coder timing events, multi-GPU hold
-  if (!b->w_dev || b->track_C || p->tslots > 0 || b->hold_coder) return onmf_step(p, b, Xt, codes, n, w, cur);
+  if (!b->w_dev || b->track_C || p->tslots > 0 || b->hold_coder) return step_streams(p, b, in, w, cur);
   cudaStream_t main = (cudaStream_t)b->main_stream, side = (cudaStream_t)b->side_stream;
-  const unsigned long long sig = buffers_sig(b);
+  const void* base = in.mb ? in.mb->base : in.Xt;
+  const void* idx = in.mb ? (const void*)in.mb->idx : nullptr;
+  const unsigned long long sig = buffers_sig(b, in.mb);
   StepGraph* e = nullptr;
   for (int i = 0; i < STEP_GRAPHS; ++i) {
     StepGraph& g = p->graphs[i];
-    if (g.last_use && g.Xt == Xt && g.codes == codes && g.n == n && g.cur == cur && g.sig == sig) { e = &g; break; }
+    if (g.last_use && g.Xt == base && g.idx == idx && g.codes == in.codes && g.n == in.n && g.cur == cur && g.sig == sig) { e = &g; break; }
   }
   if (!e) {                                       // first sight: remember the key, run the stream schedule
     StepGraph* v = &p->graphs[0];
     for (int i = 1; i < STEP_GRAPHS; ++i)
       if (p->graphs[i].last_use < v->last_use) v = &p->graphs[i];
     if (v->exec) cudaGraphExecDestroy(v->exec);
-    v->Xt = Xt; v->codes = codes; v->n = n; v->cur = cur; v->sig = sig; v->exec = nullptr; v->kernels = 0;
+    v->Xt = base; v->idx = idx; v->codes = in.codes; v->n = in.n; v->cur = cur; v->sig = sig; v->exec = nullptr; v->kernels = 0;
     v->last_use = ++p->use_clock;
-    return onmf_step(p, b, Xt, codes, n, w, cur);
+    return step_streams(p, b, in, w, cur);
   }
   e->last_use = ++p->use_clock;
   if (!e->exec) {                                 // second sight: capture
-    // everything the side stream still has in flight from stream-scheduled steps must be ordered before the capture's
-    // main-stream origin, and nothing may be captured that waits on events recorded outside the capture
-    ONMF_CUDA(cudaEventRecord(p->ev_pre, side));
-    ONMF_CUDA(cudaStreamWaitEvent(main, p->ev_pre, 0));
+    // everything the two streams still have in flight from stream-scheduled steps is ordered before the replay by the
+    // pre-launch join below; nothing is captured that waits on an event recorded outside the capture
     ONMF_CUDA(cudaStreamBeginCapture(p->cap, cudaStreamCaptureModeThreadLocal));
     long long kn = 0;
-    rc = enqueue_captured(p, b, Xt, codes, n, cur, &kn);
+    bool blended = false;
+    int rc = enqueue_step(p, b, in, cur, Blend{2, 0.0}, true, &blended, &kn);
+    if (!rc) {
+      // join: the side branch (dictionary update ...) and, unless the blend rode on the reduction, the blend after both
+      cudaError_t ce = cudaSuccess;
+      if (!blended) {
+        ce = cudaEventRecord(p->ev_g1, p->cap);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(side, p->ev_g1, 0);
+        if (ce == cudaSuccess) {
+          rc = onmf_surrogate_blend_dev(b->dtype, b->P[cur], b->k, b->d, b->w_dev, b->A, b->B, side);
+          kn += 1;
+        }
+        if (ce == cudaSuccess && !rc) ce = cudaEventRecord(p->ev_g2, side);
+      }
+      if (ce == cudaSuccess && !rc) ce = cudaStreamWaitEvent(p->cap, p->ev_g2, 0);
+      if (ce != cudaSuccess && !rc) rc = cuda_fail(ce, "step_graph: capture join");
+    }
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(p->cap, &graph);
     if (rc || ce != cudaSuccess || !graph) {
@@ -384,4 +459,22 @@ extern "C" int onmf_step_graph(onmf_step_plan* p, const onmf_step_buffers* b, co
   p->launches += e->kernels;
   ++p->graph_steps;
   return ONMF_OK;
+}
+
+extern "C" int onmf_step_graph(onmf_step_plan* p, const onmf_step_buffers* b, const void* Xt, const void* codes, int64_t n,
+                               double w, int cur) {
+  if (!p) return fail(ONMF_E_ARG, "step_graph: null plan");
+  StepIn in{Xt, nullptr, codes, n};
+  int rc = check_step_in(b, in, cur, "step_graph: bad argument");
+  if (rc) return rc;
+  return step_graph_impl(p, b, in, w, cur);
+}
+
+extern "C" int onmf_step_graph_mb(onmf_step_plan* p, const onmf_step_buffers* b, const onmf_minibatch* mb, const void* codes,
+                                  double w, int cur) {
+  if (!p || !mb) return fail(ONMF_E_ARG, "step_graph_mb: null plan / descriptor");
+  StepIn in{nullptr, mb, codes, mb->n};
+  int rc = check_step_in(b, in, cur, "step_graph_mb: bad argument");
+  if (rc) return rc;
+  return step_graph_impl(p, b, in, w, cur);
 }

@@ -79,6 +79,8 @@ class OnmfEngine:
             self.Wlo_next = torch.empty(d, k, dtype=dt_, device=dev)
             self._Whi_s = torch.empty(d, k, dtype=dt_, device=dev)
             self._Wlo_s = torch.empty(d, k, dtype=dt_, device=dev)
+        # minibatch-by-reference kernels (csrc/gemm_fused.cu): gather + widening + TF32 split inside the tensor-core kernels
+        self.fused_tc = self.use_tc and _lib.fused_tc_supported(k, d) and os.environ.get("ONMF_B200_FUSED_TC", "1") != "0"
         self.Xhi = self.Xlo = self.Hhi = self.Hlo = None
         self.stats = torch.zeros(len(_lib.STATS_FIELDS), dtype=torch.int64, device=dev)   # in-kernel work counters
         self._collect = bool(collect_stats)
@@ -223,12 +225,22 @@ class OnmfEngine:
             nbytes = max(nbytes, 64 * self.d * self.d * self.W.element_size() + 256)
         if self.use_tc:
             nbytes = max(nbytes, _lib.surrogate_tc_workspace(self._cap, self.k, self.d))
+            self.Xhi = self.Xlo = self.Hhi = self.Hlo = None      # pre-split copies: only the non-fused tensor-core path
+        if self.fused_tc:
+            nbytes = max(nbytes, _lib.surrogate_fused_tc_workspace(self._cap, self.k, self.d))
+        self._ws_sur = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._sb = None                       # the fused step's descriptor points at the old buffers
+
+    def _need_split_buffers(self):
+        """TF32 hi/lo copies of the minibatch and the codes (pre-split tensor-core kernels: k > 256, or the Python-composed
+        schedule); the fused kernels never need them."""
+        if self.use_tc and self.Xhi is None:
+            dev, dt_ = self.device, self.dtype
             self.Xhi = torch.empty(self._cap, self.d, dtype=dt_, device=dev)
             self.Xlo = torch.empty(self._cap, self.d, dtype=dt_, device=dev)
             self.Hhi = torch.empty(self._cap, self.k, dtype=dt_, device=dev)
             self.Hlo = torch.empty(self._cap, self.k, dtype=dt_, device=dev)
-        self._ws_sur = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        self._sb = None                       # the fused step's descriptor points at the old buffers
+            self._sb = None
 
     def _stats_ptr(self):
         return self.stats
@@ -240,6 +252,44 @@ class OnmfEngine:
         return 2 if k <= 32 else 5 if k <= 64 else 6
 
     # ------------------------------------------------------------------ coding only
+    def _cov_into(self, Xt, pool, idx, scale, n, W, Whi, Wlo, Ct, stream):
+        """Ct = minibatch @ W for a dense minibatch Xt or a minibatch by reference (pool, idx, scale)."""
+        if self.fused_tc:
+            src = Xt if Xt is not None else pool
+            _lib.cov_fused_tc(src, idx if Xt is None else None, n, Whi, Wlo, Ct, scale=scale if Xt is None else 1.0, stream=stream)
+            self.launches += 1
+            return
+        if Xt is None:
+            Xt = self._dense(pool, idx, scale, n, stream)
+        if self.use_tc:
+            self._need_split_buffers()
+            _lib.split_tf32(Xt, self.Xhi[:n], self.Xlo[:n], stream=stream)
+            _lib.cov_tc(self.Xhi[:n], self.Xlo[:n], Whi, Wlo, Ct, stream=stream)
+            self.launches += 2
+        else:
+            _lib.cov(Xt, W, Ct, stream=stream)
+            self.launches += 1
+
+    def _dense(self, pool, idx, scale, n, stream):
+        """materialise a minibatch by reference (engines without the fused kernels): K1 gather (+ widening)"""
+        if pool.dtype in (torch.uint8, torch.float16):
+            if idx is not None:
+                raise _lib.OnmfKernelError("narrow storage with an index needs the fused tensor-core path")
+            if getattr(self, "_wide", None) is None or self._wide.shape[0] < n:
+                self._wide = torch.empty(max(n, 1), self.d, dtype=torch.float32, device=self.device)
+            if n:
+                _lib.widen(pool[:n], scale, self._wide[:n], stream=stream)
+                self.launches += 1
+            return self._wide[:n]
+        if idx is None:
+            return pool[:n]
+        if getattr(self, "_Xg", None) is None or self._Xg.shape[0] < n:
+            self._Xg = torch.empty(max(n, 1), self.d, dtype=self.dtype, device=self.device)
+        if n:
+            _lib.gather_rows(pool, idx, self._Xg[:n], stream=stream)
+            self.launches += 1
+        return self._Xg[:n]
+
     def sparse_code(self, Xt: torch.Tensor, W: Optional[torch.Tensor] = None, alpha=None, out=None):
         """Ht (n x k) = positive lasso_lars codes of the rows of Xt (n x d) against W (default: current)."""
         n = Xt.shape[0]
@@ -256,13 +306,7 @@ class OnmfEngine:
             G = self._G_scratch
             Whi, Wlo = (self._Whi_s, self._Wlo_s) if self.use_tc else (None, None)
             self._derive(W, G, Whi, Wlo, torch.cuda.current_stream(self.device), use_ws=False)
-        if self.use_tc and n > 0:
-            _lib.split_tf32(Xt, self.Xhi[:n], self.Xlo[:n])
-            _lib.cov_tc(self.Xhi[:n], self.Xlo[:n], Whi, Wlo, Ct)
-            self.launches += 2
-        else:
-            _lib.cov(Xt, W, Ct)
-            self.launches += 1
+        self._cov_into(Xt, None, None, 1.0, n, W, Whi, Wlo, Ct, torch.cuda.current_stream(self.device))
         a = self.alpha if alpha is None else alpha
         wide = self.dtype == torch.float32 and (self._raw_W if G is self.G else
                                                 float(torch.diagonal(G).max().item()) > RAW_NORM ** 2)
@@ -294,44 +338,61 @@ class OnmfEngine:
         return self.step(Xt, t, codes=Ht)
 
     def split_buffers(self, n):
-        """(Xhi, Xlo) views of the engine-owned pre-split minibatch buffers (tensor-core path): a producer such as
-        _lib.gather_rows_split can write the minibatch straight into them and then call step(None, t, n=n)."""
+        """(Xhi, Xlo) views of the engine-owned pre-split minibatch buffers (pre-split tensor-core kernels): a producer such
+        as _lib.gather_rows_split can write the minibatch straight into them and then call step(None, t, n=n)."""
         self._reserve(max(n, 1))
+        self._need_split_buffers()
         return self.Xhi[:n], self.Xlo[:n]
+
+    def step_pool(self, pool: torch.Tensor, idx: Optional[torch.Tensor], t: float, n: Optional[int] = None, scale: float = 1.0,
+                  codes: Optional[torch.Tensor] = None):
+        """One minibatch BY REFERENCE: rows idx (int64, device; None = rows 0..n-1) of a resident sample-major pool, which
+        may be stored as float32 or -- fp32 engine on the fused tensor-core path -- uint8 / float16 (value = stored *
+        scale).  X_batch = X_unfold[:, idx] (src/ontf.py:231) is never materialised: the covariance and partial-sum
+        kernels read the pool rows in place."""
+        n = int(idx.shape[0] if idx is not None else (pool.shape[0] if n is None else n))
+        return self._step(None, (pool, idx, float(scale)), t, codes, n)
 
     def step(self, Xt: Optional[torch.Tensor], t: float, codes: Optional[torch.Tensor] = None, n: Optional[int] = None):
         """One minibatch: Xt (n_local x d) are THIS rank's columns of the minibatch, t the step index
         (w = t^-beta).  Returns the local codes Ht (view, valid until the next call).
-        Xt=None (tensor-core path only): the minibatch is already in split_buffers(n)."""
-        main, side = self.main, self.side
-        presplit = Xt is None
-        if presplit and not self.use_tc:
+        Xt=None (pre-split tensor-core kernels only): the minibatch is already in split_buffers(n)."""
+        if Xt is None and not self.use_tc:
             raise _lib.OnmfKernelError("step(None, ...) needs the tensor-core path")
-        n = Xt.shape[0] if not presplit else int(n)
+        n = Xt.shape[0] if Xt is not None else int(n)
+        return self._step(Xt, None, t, codes, n)
+
+    def _step(self, Xt, ref, t, codes, n):
+        main, side = self.main, self.side
+        presplit = Xt is None and ref is None
         self._reserve(max(n, 1))
         w = float(t) ** (-self.beta)
         cur = self._cur
+        pool, idx, scale = ref if ref is not None else (None, None, 1.0)
+        by_ref = ref is not None and self.fused_tc and self.fused and not self.track_C      # kernels read the pool in place
+        if ref is not None and not by_ref:
+            Xt = self._dense(pool, idx, scale, n, main)
+            ref = None
         if self._raw_W and codes is None:
             # first minibatch against a raw initial dictionary (fp32 engine): code it with the FP64 coder, then run the
             # normal step on those codes (aggregation + dictionary update are unaffected)
             self._raw_W = os.environ.get("ONMF_B200_WIDE_ALWAYS") == "1"      # (analysis switch: FP64 coder at every step)
             if n > 0:
-                main_ = self.main
                 Ct, Ht = self.Ct[:n], self.Ht[:n]
-                if self.use_tc:
-                    if not presplit:
-                        _lib.split_tf32(Xt, self.Xhi[:n], self.Xlo[:n], stream=main_)
-                        self.launches += 1
-                    _lib.cov_tc(self.Xhi[:n], self.Xlo[:n], self.Whi, self.Wlo, Ct, stream=main_)
+                if presplit:
+                    _lib.cov_tc(self.Xhi[:n], self.Xlo[:n], self.Whi, self.Wlo, Ct, stream=main)
+                    self.launches += 1
                 else:
-                    _lib.cov(Xt, self.W, Ct, stream=main_)
-                self.launches += 1
-                self._lars_wide(self.G, Ct, self.alpha, Ht, main_)
+                    self._cov_into(Xt, pool, idx, scale, n, self.W, getattr(self, "Whi", None), getattr(self, "Wlo", None), Ct, main)
+                self._lars_wide(self.G, Ct, self.alpha, Ht, main)
                 codes = Ht
         if os.environ.get("ONMF_B200_WIDE_ALWAYS") != "1":
             self._raw_W = False
         if self.fused:
-            return self._step_fused(Xt, codes, n, w, cur)
+            return self._step_fused(Xt, ref, codes, n, w, cur)
+        # ---- Python-composed schedule (analysis: bench.py --timeline; same kernels as the pre-split C path) ----
+        if self.use_tc:
+            self._need_split_buffers()
         # side stream: dictionary update for this step with the OLD aggregates (src/ontf.py:151).  It is
         # queued behind the previous step's all-reduce + blend (same stream), and must not overwrite the
         # buffer the previous coding was still reading.
@@ -357,17 +418,14 @@ class OnmfEngine:
                     _lib.cov_tc(Xhi, Xlo, self.Whi, self.Wlo, Ct, stream=main)
                 else:
                     _lib.cov(Xt, self.W, Ct, stream=main)
-                # The coder is a persistent kernel that owns every SM it runs on.  When it is short (few columns per
-                # GPU) the dictionary update on the side stream would otherwise queue behind it and land on the critical
-                # path; leaving one cluster's worth of SMs free lets the two overlap (costs the coder 8/148 of its rate).
                 if self.world > 1:
                     # The dictionary update is one thread-block cluster: it can only be placed while a whole group of SMs
-                    # in one GPC is free, i.e. BEFORE the persistent coder has spread over the GPU (the SMs the coder leaves
-                    # free are scattered).  On one GPU it is queued at the start of the step and wins that race; across
-                    # GPUs it waits for the all-reduce of the previous partial sums, so hold the coder back until that has
-                    # landed: both become runnable together and the high-priority side stream is placed first.
+                    # in one GPC is free, i.e. BEFORE the persistent coder has spread over the GPU.  On one GPU it is queued
+                    # at the start of the step and wins that race; across GPUs it waits for the all-reduce of the previous
+                    # partial sums, so hold the coder back until that has landed: both become runnable together and the
+                    # high-priority side stream is placed first (the coder's last CTAs start when the update retires).
                     main.wait_event(self._ev_AB)
-                rsv = self.reserve_sms if self.reserve_sms is not None else (8 if n * self.k <= 131072 * 256 else 0)
+                rsv = self.reserve_sms if self.reserve_sms is not None else 0
                 saved = _lib.get_option(_lib.OPT_LARS_RESERVED_SMS)
                 _lib.set_option(_lib.OPT_LARS_RESERVED_SMS, rsv)
                 try:
@@ -421,8 +479,8 @@ class OnmfEngine:
         self._cur ^= 1
         return Ht
 
-    def _step_fused(self, Xt, codes, n, w, cur):
-        """the same schedule through ONE call into libonmf_b200.so (onmf_step / onmf_step_launch + onmf_step_finish)"""
+    def _step_fused(self, Xt, ref, codes, n, w, cur):
+        """the same schedule through ONE call into libonmf_b200.so (onmf_step[_mb] / onmf_step_launch[_mb] + onmf_step_finish)"""
         for t_, nm in ((Xt, "Xt"), (codes, "codes")):
             if t_ is not None:
                 _lib._req(t_, nm, self.dtype)
@@ -430,16 +488,32 @@ class OnmfEngine:
             raise _lib.OnmfKernelError("codes must be (n x k)")
         if Xt is not None and Xt.shape[1] != self.d:
             raise _lib.OnmfKernelError("Xt must be (n x d)")
+        mb = None
+        if ref is not None:
+            pool, idx, scale = ref
+            if pool.shape[1] != self.d:
+                raise _lib.OnmfKernelError("pool must be (n_pool x d)")
+            mb = _lib.make_minibatch(pool, idx, n, scale)
+        elif Xt is not None and self.fused_tc and not self.track_C:
+            mb = _lib.make_minibatch(Xt, None, n, 1.0)          # a dense minibatch is a pool read front to back
+            Xt = None
+        elif self.use_tc:
+            self._need_split_buffers()                           # pre-split tensor-core kernels (k > 256, track_C)
         if self._sb is None:
             self._make_bufs()
         if self.world > 1:
             import torch.distributed as dist
-            self._plan.launch(self._sb, Xt, codes, n, cur)
+            if mb is not None:
+                self._plan.launch_mb(self._sb, mb, codes, cur)
+            else:
+                self._plan.launch(self._sb, Xt, codes, n, cur)
             with torch.cuda.stream(self.side):
                 dist.all_reduce(self.P[cur], group=self.pg)
                 if self.track_C:
                     dist.all_reduce(self.P2, group=self.pg)
             self._plan.finish(self._sb, w, cur)
+        elif mb is not None:
+            self._plan.step_mb(self._sb, mb, codes, w, cur, graph=self.graph)
         elif self.graph:
             self._plan.step_graph(self._sb, Xt, codes, n, w, cur)
         else:
@@ -458,8 +532,8 @@ class OnmfEngine:
 
         Xt_host may be float32 / float64 (the engine's dtype), or a narrower STORAGE format -- uint8 (scale defaults to
         1/255, the reference's `data / 255`, image_reconstruction.py:88) or float16 (scale 1) -- which crosses PCIe at a
-        quarter / half of the bytes and is widened to fp32 on the device (onmf_widen, fused with the TF32 hi/lo split on
-        the tensor-core path); arithmetic is fp32 either way.
+        quarter / half of the bytes; on the fused tensor-core path the kernels read the staged bytes as they are (widening
+        inside the loaders), otherwise onmf_widen expands them once.  Arithmetic is fp32 either way.
 
         The host->device copy runs on a copy stream into one of two staging buffers, so the copy of minibatch t+1 overlaps
         the coding of minibatch t; if W_out_host (pinned, d x k) is given the updated dictionary is copied back
@@ -472,15 +546,14 @@ class OnmfEngine:
         narrow = sdt in (torch.uint8, torch.float16)
         if not narrow and sdt != self.dtype:
             raise _lib.OnmfKernelError("step_host: minibatch dtype %s (engine %s; uint8 / float16 storage also accepted)" % (sdt, self.dtype))
-        if narrow and (self.dtype != torch.float32 or (n * self.d) % 4):
-            raise _lib.OnmfKernelError("step_host: uint8 / float16 storage needs the fp32 engine and n*d % 4 == 0")
+        if narrow and (self.dtype != torch.float32 or self.d % 4):
+            raise _lib.OnmfKernelError("step_host: uint8 / float16 storage needs the fp32 engine and d % 4 == 0")
         if not hasattr(self, "_stage") or self._stage[0].shape[0] < n or self._stage[0].dtype != sdt:
             self._stage = [torch.empty(max(n, 1), self.d, dtype=sdt, device=self.device) for _ in range(2)]
             self._stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
             self._stage_i = 0
             self._copy = torch.cuda.Stream(self.device)
             self._ev_h2d = torch.cuda.Event()
-            self._wide = None
         i = self._stage_i
         self._stage_i ^= 1
         buf = self._stage[i][:n]
@@ -491,24 +564,10 @@ class OnmfEngine:
         self.main.wait_event(self._ev_h2d)
         if narrow:
             sc = (1.0 / 255.0 if sdt == torch.uint8 else 1.0) if scale is None else float(scale)
-            if self.use_tc:
-                hi, lo = self.split_buffers(n)
-                if n:
-                    _lib.widen(buf, sc, hi, lo, stream=self.main)
-                    self.launches += 1
-                self._stage_ev[i].record(self.main)        # the staging buffer is free as soon as it has been widened
-                Ht = self.step(None, t, n=n)
-            else:
-                if self._wide is None or self._wide.shape[0] < n:
-                    self._wide = torch.empty(max(n, 1), self.d, dtype=torch.float32, device=self.device)
-                if n:
-                    _lib.widen(buf, sc, self._wide[:n], stream=self.main)
-                    self.launches += 1
-                self._stage_ev[i].record(self.main)
-                Ht = self.step(self._wide[:n], t)
+            Ht = self.step_pool(self._stage[i], None, t, n=n, scale=sc)
         else:
             Ht = self.step(buf, t)
-            self._stage_ev[i].record(self.main)
+        self._stage_ev[i].record(self.main)
         if W_out_host is not None:
             with torch.cuda.stream(self.side):
                 W_out_host.copy_(self.W, non_blocking=True)     # self.W is the dictionary this step produced

@@ -208,6 +208,12 @@ class Online_NMF():
             if self.subsample:
                 if idx_all is not None:
                     idx = idx_all[i - 1]
+                    if self.coder == "lasso_lars" and not shipped:
+                        # X_batch = X[:, idx] (src/onmf.py:213) by reference: the kernels read the pool rows in place
+                        Ht = eng.step_pool(pool, idx_dev[i - 1], float(t0 + i))
+                        self.history = np.float64(t0 + i) + 1
+                        code[:, idx[lo:hi]] += _host.from_sample_major(Ht)        # src/onmf.py:221 (this rank's columns)
+                        continue
                     _lib.gather_rows(pool, idx_dev[i - 1], Xb)
                 else:
                     idx = np.random.randint(n, size=self.batch_size)      # src/onmf.py:212

@@ -167,15 +167,13 @@ class Online_NTF():
         m = self.batch_size if self.subsample else n
         lo, hi = shard_range(m, world, rank)           # this rank's columns of every minibatch (contiguous block)
         idx_d = _host.upload_indices(idx_all[:, lo:hi], dev) if idx_all is not None else None
-        Xb = torch.empty(hi - lo, d, dtype=self._dtype, device=dev) if self.subsample else None
         for s_ in range(steps):
             i = s_ + 1
             if self.subsample:
-                _lib.gather_rows(pool, idx_d[s_], Xb)                  # X_batch = X_unfold[:, idx], src/ontf.py:231
-                Xt = Xb
+                # X_batch = X_unfold[:, idx] (src/ontf.py:231) by reference: the kernels read the pool rows in place
+                eng.step_pool(pool, idx_d[s_], float(t0 + i))
             else:
-                Xt = pool[lo:hi]
-            eng.step(Xt, float(t0 + i))
+                eng.step(pool[lo:hi], float(t0 + i))
             self.history = np.float64(t0 + i) + 1
         Wd, Ad, Bd, _ = eng.state()
         self.lars_stats = eng.read_stats()

@@ -567,9 +567,11 @@ def test_surrogate_error_readout(golden_dir):
         assert abs(got - ref) <= tol * scale, (got, ref)
 
 
-def test_fused_step_equals_python_composed_schedule():
+def test_fused_step_equals_python_composed_schedule(monkeypatch):
     """OnmfEngine(fused=True) (one onmf_step call per minibatch) and fused=False (the same kernels composed from Python
-    with torch events) must give bitwise identical state, in both precisions and with external codes / track_C."""
+    with torch events) must give bitwise identical state, in both precisions and with external codes / track_C.
+    (Both on the pre-split tensor-core kernels: the Python-composed schedule does not use the minibatch-by-reference ones.)"""
+    monkeypatch.setenv("ONMF_B200_FUSED_TC", "0")
     rng = np.random.default_rng(7)
     d, k, n = 64, 32, 777
     X = rng.random((n, d)); W0 = rng.random((d, k))
@@ -858,3 +860,29 @@ def test_fused_tensor_core_products_vs_fp64(n, d, k, n_pool):
     bad = idx.clone(); bad[0] = n_pool + 5
     _lib.cov_fused_tc(pool, bad, n, Wh, Wl, Cf)
     assert torch.isnan(Cf[0]).all() and not torch.isnan(Cf[1:]).any()
+
+
+def test_minibatch_by_reference_engine_matches_presplit_engine(monkeypatch, golden_dir):
+    """The production fp32 step with the minibatch passed by reference (gemm_fused.cu: gather + TF32 split inside the
+    tensor-core kernels, blend fused into the reduction) against the pre-split tensor-core kernels and the golden run."""
+    g = load(golden_dir, "cfg4_ising_pm1")
+    X, W0 = g["X"], g["W0"]
+    pool = tt(X.T, torch.float32)
+    outs = []
+    for fused_tc in ("1", "0"):
+        monkeypatch.setenv("ONMF_B200_FUSED_TC", fused_tc)
+        eng = OnmfEngine(400, 100, alpha=1.0, dtype=torch.float32, device=dev(), collect_stats=True)
+        assert eng.use_tc and eng.fused_tc == (fused_tc == "1")
+        eng.set_state(W0)
+        for i in range(int(g["n_steps"])):
+            idx = torch.from_numpy(g["idx"][i].astype(np.int64)).to(dev())
+            H = eng.step_pool(pool, idx, float(i + 1))
+            if i > 0:
+                assert rel(H.cpu().numpy().T, g["H_%d" % i]) < CODE_TOL_FP32
+        W, A, B, _ = eng.state()
+        torch.cuda.synchronize()
+        outs.append((W.cpu().numpy().astype(np.float64), A.cpu().numpy().astype(np.float64)))
+        assert per_atom(outs[-1][0], g["W_final"]) < ATOM_TOL_FP32
+        if fused_tc == "1":
+            assert eng.Xhi is None and eng.Hhi is None          # no hi/lo copies of the minibatch or the codes exist
+    assert per_atom(outs[0][0], outs[1][0]) < 5e-4 and rel(outs[0][1], outs[1][1]) < 1e-4
