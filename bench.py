@@ -246,14 +246,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # fresh minibatch per step: the pool resampled with replacement.  Like the reference-facing classes (which draw every
+    # step's np.random.randint up front, src/ontf.py:230), the index sequence of the whole run is drawn before the timed
+    # region; two index buffers alternate so that a step's (pool, idx) key is stable for the CUDA-graph replay.
+    n_seq = Wm + K + 64
+    idx_all = torch.randint(0, n, (n_seq, n), device=dev, generator=gen)
     idx_buf = [torch.empty(n, dtype=torch.int64, device=dev) for _ in range(2)]
 
     def one_step(t, eng=eng):
-        # fresh minibatch: resample the pool (with replacement); the step takes the minibatch BY REFERENCE (pool + indices):
-        # on the fused tensor-core path K1 (gather) happens inside the covariance / partial-sum kernels, otherwise the
-        # engine runs the K1 gather kernel first
-        idx = idx_buf[t & 1]
-        torch.randint(0, n, (n,), device=dev, generator=gen, out=idx)
+        # the step takes the minibatch BY REFERENCE (pool + indices): on the fused tensor-core path K1 (gather) happens
+        # inside the covariance / partial-sum kernels, otherwise the engine runs the K1 gather kernel first
+        if graph_mode:
+            idx = idx_buf[t & 1]
+            idx.copy_(idx_all[t % n_seq])
+        else:
+            idx = idx_all[t % n_seq]
         eng.step_pool(pool, idx, float(t))
 
     t = 0

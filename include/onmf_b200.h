@@ -48,6 +48,8 @@ int onmf_get_option(int key, int* value);
 int onmf_version(void);                      /* 100*major + minor                                   */
 const char* onmf_last_error(void);
 int onmf_built_arch(void);                   /* 100 => sm_100a                                      */
+long long onmf_launch_count(void);           /* kernels launched so far by the calling host thread (every launch site of
+                                                the library counts itself; graph replays count their kernel nodes) */
 
 /* ---------------------------------------------------------------------------------------------
  * K1  patch gather / matricization

@@ -36,6 +36,7 @@ SIGNATURES = {
     "onmf_version": (_i, []),
     "onmf_last_error": (ctypes.c_char_p, []),
     "onmf_built_arch": (_i, []),
+    "onmf_launch_count": (ctypes.c_longlong, []),
     "onmf_gather_patches": (_i, [_i, _vp, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp]),
     "onmf_gather_rows": (_i, [_i, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "onmf_transpose": (_i, [_i, _i, _vp, _i64, _i64, _vp, _vp]),
@@ -240,6 +241,11 @@ MAX_COMPONENTS = 512          # largest n_components the LARS coder is instantia
 
 def set_option(key, value):
     _check(load().onmf_set_option(int(key), int(value)), "onmf_set_option")
+
+
+def launch_count():
+    """kernels launched so far by this host thread through the library (graph replays count their kernel nodes)"""
+    return int(load().onmf_launch_count())
 
 
 def get_option(key):

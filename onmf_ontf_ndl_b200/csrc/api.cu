@@ -3,12 +3,14 @@
 
 namespace onmf {
 thread_local char g_err[512] = "";
+thread_local long long g_launches = 0;
 thread_local int g_lars_reserved_sms = 0;   // per host thread, like the error string: engines on different threads do not interfere
 }
 
 extern "C" int onmf_version(void) { return 100; }
 extern "C" const char* onmf_last_error(void) { return onmf::g_err; }
 extern "C" int onmf_built_arch(void) { return 100; }
+extern "C" long long onmf_launch_count(void) { return onmf::g_launches; }
 
 extern "C" int onmf_set_option(int key, int value) {
   switch (key) {

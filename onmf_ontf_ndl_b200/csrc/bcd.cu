@@ -12,6 +12,7 @@
 // barrier.cluster per atom, partials summed in rank order so all CTAs -- and all GPUs of a
 // data-parallel run -- get bit-identical dictionaries).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -67,30 +68,32 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
   if (k > 1) issue_col(1);
   T bcur = has_row ? B[(size_t)0 * d + row0 + rl] : T(0);
 
-  // W A[:,j] and B[j,:] are O(A_jj) while their difference is the O(1e-2 .. 1e-4) update: accumulated in the working
-  // precision the cancellation amplifies fp32 rounding ~1e4x.  The products of fp32 numbers are exact in FP64, so the dot
-  // product and the difference are formed in FP64 in both modes.
-  // team dot product of this row with column `a` of A, leaving out index `skip` (-1: none)
-  auto team_dot = [&](const T* a, int skip) -> double {
-    double acc0 = 0.0, acc1 = 0.0;
+  // W A[:,j] and B[j,:] are O(A_jj) while their difference is the O(1e-2 .. 1e-4) update.  Every lane sums its k/tpr
+  // products in the working precision (two independent chains); the partial sums are combined across the team, and the
+  // difference with B is formed, in FP64.  (Accumulating every product in FP64 costs two f32->f64 conversions per product
+  // on the quarter-rate conversion pipe: measured 0.81 -> 1.32 ms at d=1024, k=256 -- ncu: XU pipe 46 % -- for no
+  // measurable change of the dictionary; profiles/r2_other_kernels_ncu.md.)
+  // team dot product of this row with column `a` of A (whatever the shared-memory slab holds at the moment)
+  auto team_dot = [&](const T* a) -> double {
+    T acc0 = T(0), acc1 = T(0);
     if (has_row) {
       int q = tl;
       for (; q + tpr < k; q += 2 * tpr) {
-        if (q != skip) acc0 += (double)wrow[q] * (double)a[q];
-        if (q + tpr != skip) acc1 += (double)wrow[q + tpr] * (double)a[q + tpr];
+        acc0 += wrow[q] * a[q];
+        acc1 += wrow[q + tpr] * a[q + tpr];
       }
-      if (q < k && q != skip) acc0 += (double)wrow[q] * (double)a[q];
+      if (q < k) acc0 += wrow[q] * a[q];
     }
-    double dsum = acc0 + acc1;
+    double dsum = (double)acc0 + (double)acc1;
     for (int off = tpr >> 1; off > 0; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
     return dsum;
   };
-  double dot = team_dot(aj, -1);                 // atom 0: nothing pending
+  double dot = team_dot(aj);                     // atom 0: nothing pending
 
   // Software pipeline over atoms.  Column j of W is final only after the cluster-wide norm of its new entries; column
   // j+1's dot product needs it in ONE term (W[row, j] A[j, j+1]).  So the norm reduction of atom j (DSMEM pushes + one
-  // split-phase barrier.cluster) is in flight while every team already forms the rest of atom j+1's dot product; the
-  // scaled term is added after the barrier.  Column j+1 of A (strided, L2 resident) and B[j+1, row] are requested one
+  // split-phase barrier.cluster) is in flight while every team already forms atom j+1's dot product with the OLD entry
+  // W[row, j] still in the slab; after the barrier that one term is exchanged: dot += (w_final - w_old) A[j, j+1].  Column j+1 of A (strided, L2 resident) and B[j+1, row] are requested one
   // full atom step before they are consumed.
   for (int j = 0; j < k; ++j) {
     const int par = j & 1;
@@ -101,10 +104,11 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
       if (has_row) bnext = B[(size_t)(j + 1) * d + row0 + rl];
     }
     if (j + 2 < k) issue_col(j + 2);
-    T wnew = T(0);
+    T wnew = T(0), wold = T(0);
     if (has_row) {
+      wold = wrow[j];
       const double c = 1.0 / ((double)a[j] + 1.0);
-      const double v = (double)wrow[j] - c * (dot - (double)bcur);
+      const double v = (double)wold - c * (dot - (double)bcur);
       wnew = v > 0.0 ? (T)v : T(0);
     }
     bcur = bnext;
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
     cluster.barrier_arrive();                      // release: the pushes above are visible to whoever passes the wait
     // ---- in the shadow of the reduction: atom j+1's dot product without its j-th term ----
     double pdot = 0.0;
-    if (j + 1 < k) pdot = team_dot(an, j);
+    if (j + 1 < k) pdot = team_dot(an);           // (the team's lanes share a warp: these reads precede the write below)
     cluster.barrier_wait();
     T tot = T(0);
     for (int r = 0; r < csize; ++r) tot += slots[par * BCD_MAX_CLUSTER + r];
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
     const T sc = T(1) / (nrm > T(1) ? nrm : T(1));
     const T wfin = sc * wnew;
     if (has_row && tl == 0) Ws[(size_t)rl * ks + j] = wfin;
-    if (j + 1 < k) dot = pdot + (has_row ? (double)wfin * (double)an[j] : 0.0);
+    if (j + 1 < k) dot = pdot + (has_row ? ((double)wfin - (double)wold) * (double)an[j] : 0.0);
     __syncwarp();
   }
   __syncthreads();
@@ -222,6 +226,7 @@ static int update_dict_global_t(const T* Win, const T* A, const T* B, int d, int
   T* partials = (T*)ws;
   void* args[] = {(void*)&Win, (void*)&A, (void*)&B, (void*)&Wout, (void*)&d, (void*)&k, (void*)&rpb, (void*)&partials};
   ONMF_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(nb), dim3(256), args, smem, st));
+  ++g_launches;
   return ONMF_OK;
 }
 
@@ -249,8 +254,12 @@ static int update_dict_t(const T* Win, const T* A, const T* B, int d, int k, T* 
     if (cs > BCD_MAX_CLUSTER) return fail(ONMF_E_UNSUPPORTED, "update_dict: d*k too large for one 16-CTA cluster");
     rpc = cdiv(d, cs);
     tpr = 32;
-    while (tpr > 1 && rpc * tpr > 1024) tpr >>= 1;
+    while (tpr > 1 && rpc * tpr > 512) tpr >>= 1;    // 512 threads per CTA: 16 warps to synchronise per atom (measured 9 % faster than 1024)
     while (tpr > 1 && tpr * 2 > k) tpr >>= 1;
+    {
+      static const int tpr_cap = [] { const char* e = getenv("ONMF_BCD_TPR"); return e ? atoi(e) : 0; }();   // (experiments)
+      while (tpr_cap > 0 && tpr > tpr_cap) tpr >>= 1;
+    }
     ks = round_up(k, 32) + (tpr < 32 ? tpr : 1);
     smem = ((size_t)rpc * ks + 2 * (size_t)k + 32 + 2 * BCD_MAX_CLUSTER) * sizeof(T);
     bool fits = smem <= smem_cap && rpc <= 1024;
@@ -275,6 +284,7 @@ static int update_dict_t(const T* Win, const T* A, const T* B, int d, int k, T* 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ONMF_CUDA(cudaLaunchKernelEx(&cfg, kern, Win, A, B, Wout, d, k, rpc, ks, tpr));
+  ++g_launches;
   return ONMF_OK;
 }
 

@@ -11,6 +11,7 @@ namespace onmf {
 
 extern thread_local char g_err[512];
 extern thread_local int g_lars_reserved_sms;     // SMs the persistent coder leaves free for concurrently running kernels
+extern thread_local long long g_launches;        // kernels launched by this host thread (every launch site counts itself)
 
 inline int fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -32,6 +33,7 @@ inline int cuda_fail(cudaError_t e, const char* where) {
   do {                                                             \
     cudaError_t e__ = cudaGetLastError();                          \
     if (e__ != cudaSuccess) return onmf::cuda_fail(e__, where);    \
+    ++onmf::g_launches;                                            \
   } while (0)
 
 inline int num_sms() {

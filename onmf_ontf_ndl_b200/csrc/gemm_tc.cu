@@ -500,6 +500,7 @@ extern "C" int onmf_surrogate_partial_tc(const void* Ht_hi, const void* Ht_lo, c
   int w2 = tc::dispatch_bn<true, true>(A, B2, n, part2, d, s2, (long long)k * d, st);
   if (w2 < 0) return w2;
   tc::split_reduce2d_kernel<<<(unsigned)cdiv<long long>((long long)k * k, 256), 256, 0, st>>>(part1, w1, k, k, Pf, ldp);
+  ONMF_LAUNCH_CHECK("split_reduce2d_kernel");
   tc::split_reduce2d_kernel<<<(unsigned)cdiv<long long>((long long)k * d, 256), 256, 0, st>>>(part2, w2, k, d, Pf + k, ldp);
   ONMF_LAUNCH_CHECK("split_reduce2d_kernel");
   return ONMF_OK;

@@ -985,8 +985,10 @@ static size_t ovf_scratch_groups(int kp) {
   return g;
 }
 
+// *padded: whether the zero-padded global copy of G (P.Gp) has been written in this call; a tier that cannot stage G in
+// shared memory writes it on first need (the small classes in fp32 never do: a launch less on their launch-bound steps)
 template <typename T, int LPC, int NA, int SMAX, bool MGLOB, int SPLIT = 0>
-static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaStream_t st) {
+static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaStream_t st, bool* padded) {
   constexpr int GPW = 32 / LPC;
   const int k = P.k;
   const int smem_max = max_smem_optin();
@@ -1014,6 +1016,12 @@ static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaSt
     if (grid > cap) grid = (int)cap;
   }
   size_t smem = (gsm ? g_bytes : 0) + (size_t)nw * GPW * grp_bytes;
+  if (!gsm && !*padded) {
+    constexpr int KPAD = LPC * NA;
+    pad_gram_kernel<T><<<cdiv(k * KPAD, 256), 256, 0, st>>>(P.G, P.G64, k, KPAD, const_cast<T*>(P.Gp));
+    ONMF_LAUNCH_CHECK("pad_gram_kernel");
+    *padded = true;
+  }
   if (gsm) {
     auto kern = lars_kernel<T, LPC, NA, SMAX, true, MGLOB, SPLIT>;
     ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1055,8 +1063,7 @@ static int launch_class(const T* G, const double* G64, const T* Ct, long long n,
   double* mhyb = reinterpret_cast<double*>(ws + sizeof(LarsWs) + 2 * lb + ws_gp_bytes(k, KP));
   double* mscr = reinterpret_cast<double*>(ws + sizeof(LarsWs) + 2 * lb + ws_gp_bytes(k, KP) + ws_hyb_bytes(KP));
   ONMF_CUDA(cudaMemsetAsync(hdr, 0, LARS_WS_RESET_BYTES, st));   // everything but the persistent hint
-  pad_gram_kernel<T><<<cdiv(k * KP, 256), 256, 0, st>>>(G, G64, k, KP, gp);
-  ONMF_LAUNCH_CHECK("pad_gram_kernel");
+  bool padded = false;
 
   LarsParams<T> P;
   P.G = G; P.G64 = G64; P.Gp = gp; P.Ct = Ct; P.Ht = Ht; P.n = n; P.k = k; P.d = d; P.max_iter = max_iter;
@@ -1082,27 +1089,27 @@ static int launch_class(const T* G, const double* G64, const T* Ct, long long n,
   if (adaptive || first == 0) {
     LarsParams<T> Q = tier_params(0, 0, false, S1 > 0, GL && S1 == 0);
     if (adaptive) { Q.hint = &hdr->hint; Q.run_if = 0; }
-    rc = launch_tier<T, LPC, NA, S0, (GL && S1 == 0), SPLIT0>(Q, n, 32, st);
+    rc = launch_tier<T, LPC, NA, S0, (GL && S1 == 0), SPLIT0>(Q, n, 32, st, &padded);
     if (rc) return rc;
   }
   if constexpr (S1 > 0) {
     if (adaptive || first == 1) {      // tier 1 over ALL columns
       LarsParams<T> Q = tier_params(1, 4, false, S2 > 0, GL && S2 == 0);
       if (adaptive) { Q.hint = &hdr->hint; Q.run_if = 1; Q.over_thresh = &hdr->over_thresh; }
-      rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(Q, n, (GL && S2 == 0) ? 2 : 32, st);
+      rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(Q, n, (GL && S2 == 0) ? 2 : 32, st, &padded);
       if (rc) return rc;
     }
     if (adaptive || first == 0) {      // tier 1 over tier 0's overflow list
-      rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(tier_params(1, 1, true, S2 > 0, GL && S2 == 0), n, (GL && S2 == 0) ? 2 : 32, st);
+      rc = launch_tier<T, LPC, NA, S1, (GL && S2 == 0)>(tier_params(1, 1, true, S2 > 0, GL && S2 == 0), n, (GL && S2 == 0) ? 2 : 32, st, &padded);
       if (rc) return rc;
     }
   }
   if constexpr (S2 > 0) {
-    rc = launch_tier<T, LPC, NA, S2, (GL && S3 == 0)>(tier_params(2, 2, true, S3 > 0, GL && S3 == 0), n, (GL && S3 == 0) ? 2 : 32, st);
+    rc = launch_tier<T, LPC, NA, S2, (GL && S3 == 0)>(tier_params(2, 2, true, S3 > 0, GL && S3 == 0), n, (GL && S3 == 0) ? 2 : 32, st, &padded);
     if (rc) return rc;
   }
   if constexpr (S3 > 0) {
-    rc = launch_tier<T, LPC, NA, S3, GL>(tier_params(3, 3, true, false, GL), n, GL ? 2 : 32, st);
+    rc = launch_tier<T, LPC, NA, S3, GL>(tier_params(3, 3, true, false, GL), n, GL ? 2 : 32, st, &padded);
     if (rc) return rc;
   }
   if (adaptive) {

@@ -127,8 +127,6 @@ extern "C" int onmf_step_plan_lars_ms(onmf_step_plan* p, float* out, int max_out
   return ONMF_OK;
 }
 
-static int lars_launch_count(int k) { return k <= 32 ? 2 : k <= 64 ? 5 : 6; }   // pad + tier chain + hint (lars.cu)
-
 static int check_buffers(const onmf_step_buffers* b, bool need_code_bufs) {
   if (!b) return fail(ONMF_E_ARG, "step: null buffers");
   if (b->dtype != ONMF_F32 && b->dtype != ONMF_F64) return fail(ONMF_E_ARG, "step: bad dtype");
@@ -172,7 +170,7 @@ static int enqueue_step(onmf_step_plan* p, const onmf_step_buffers* b, const Ste
   const bool fused = mb_fused(b, in);
   const bool presplit = (in.Xt == nullptr && in.mb == nullptr);
   int rc;
-  long long kn = 0;
+  const long long l0 = g_launches;
   *blended = false;
 
   // ---- side: dictionary update with the OLD aggregates, then everything the coder derives from the dictionary ----
@@ -185,10 +183,8 @@ static int enqueue_step(onmf_step_plan* p, const onmf_step_buffers* b, const Ste
   // (the large-dictionary fallback of the update borrows the Gram workspace: same stream, used one after the other)
   if ((rc = onmf_update_dict_ws(dt, b->W[cur], b->A, b->B, d, k, b->W[nx], b->ws_gram, b->ws_gram_bytes, side))) return rc;
   if ((rc = onmf_gram_f64(dt, b->W[nx], d, k, b->G[nx], nullptr, b->ws_gram, b->ws_gram_bytes, side))) return rc;
-  kn += 3;
   if (b->use_tc) {
     if ((rc = onmf_split_tf32(b->W[nx], b->Whi[nx], b->Wlo[nx], (int64_t)d * k, side))) return rc;
-    kn += 1;
   }
   ONMF_CUDA(cudaEventRecord(captured ? p->ev_g2 : p->ev_W, side));
 
@@ -200,7 +196,6 @@ static int enqueue_step(onmf_step_plan* p, const onmf_step_buffers* b, const Ste
     const void* Hcodes = in.codes ? in.codes : b->Ht;
     if (b->use_tc && !fused && !presplit) {
       if ((rc = onmf_split_tf32(in.Xt, b->Xhi, b->Xlo, n * d, main))) return rc;
-      kn += 1;
     }
     if (!in.codes) {
       if (!b->Ct || !b->ws_lars) return fail(ONMF_E_ARG, "step: null coder buffer");
@@ -230,7 +225,6 @@ static int enqueue_step(onmf_step_plan* p, const onmf_step_buffers* b, const Ste
         ONMF_CUDA(cudaEventRecord(p->t1[p->tcount % p->tslots], main));
         ++p->tcount;
       }
-      kn += 1 + lars_launch_count(k);
     }
     if (fused) {
       if (fuse_blend) {
@@ -244,25 +238,21 @@ static int enqueue_step(onmf_step_plan* p, const onmf_step_buffers* b, const Ste
                                      b->P[cur], 0, 0.0, nullptr, nullptr, nullptr, b->ws_sur, b->ws_sur_bytes, main);
       }
       if (rc) return rc;
-      kn += 2;
     } else if (b->use_tc) {
       if ((rc = onmf_split_tf32(Hcodes, b->Hhi, b->Hlo, n * k, main))) return rc;
       if ((rc = onmf_surrogate_partial_tc(b->Hhi, b->Hlo, b->Xhi, b->Xlo, n, k, d, b->P[cur], b->ws_sur, b->ws_sur_bytes, main)))
         return rc;
-      kn += 5;
     } else {
       if ((rc = onmf_surrogate_partial(dt, Hcodes, in.Xt, n, k, d, b->P[cur], b->ws_sur, b->ws_sur_bytes, main))) return rc;
-      kn += 3;
     }
     if (b->track_C) {
       if ((rc = onmf_xxt_partial(dt, in.Xt, n, d, b->P2, b->ws_sur, b->ws_sur_bytes, main))) return rc;
-      kn += 2;
     }
   } else {
     ONMF_CUDA(cudaMemsetAsync(b->P[cur], 0, (size_t)k * (k + d) * esz, main));
     if (b->track_C) ONMF_CUDA(cudaMemsetAsync(b->P2, 0, (size_t)d * d * esz, main));
   }
-  *kernels = kn;
+  *kernels = g_launches - l0;
   return ONMF_OK;
 }
 
@@ -299,14 +289,14 @@ static int launch_streams(onmf_step_plan* p, const onmf_step_buffers* b, const S
 static int finish_streams(onmf_step_plan* p, const onmf_step_buffers* b, double w, int cur, bool blended) {
   cudaStream_t main = (cudaStream_t)b->main_stream, side = (cudaStream_t)b->side_stream;
   int rc;
+  const long long l0 = g_launches;
   if (!blended) {
     if ((rc = onmf_surrogate_blend(b->dtype, b->P[cur], b->k, b->d, w, b->A, b->B, side))) return rc;
-    p->launches += 1;
   }
   if (b->track_C) {
     if ((rc = onmf_axpby(b->dtype, (int64_t)b->d * b->d, w, b->P2, 1.0 - w, b->C, side))) return rc;
-    p->launches += 1;
   }
+  p->launches += g_launches - l0;
   ONMF_CUDA(cudaEventRecord(p->ev_AB, side));        // (blended on main: side has waited for ev_P, recorded after that blend)
   ONMF_CUDA(cudaStreamWaitEvent(main, p->ev_W, 0));  // the next coding needs the new dictionary only
   return ONMF_OK;
@@ -416,6 +406,7 @@ static int step_graph_impl(onmf_step_plan* p, const onmf_step_buffers* b, const 
     ONMF_CUDA(cudaStreamBeginCapture(p->cap, cudaStreamCaptureModeThreadLocal));
     long long kn = 0;
     bool blended = false;
+    const long long l0 = g_launches;              // launches recorded into the graph are counted when it is replayed
     int rc = enqueue_step(p, b, in, cur, Blend{2, 0.0}, true, &blended, &kn);
     if (!rc) {
       // join: the side branch (dictionary update ...) and, unless the blend rode on the reduction, the blend after both
@@ -425,13 +416,14 @@ static int step_graph_impl(onmf_step_plan* p, const onmf_step_buffers* b, const 
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(side, p->ev_g1, 0);
         if (ce == cudaSuccess) {
           rc = onmf_surrogate_blend_dev(b->dtype, b->P[cur], b->k, b->d, b->w_dev, b->A, b->B, side);
-          kn += 1;
         }
         if (ce == cudaSuccess && !rc) ce = cudaEventRecord(p->ev_g2, side);
       }
       if (ce == cudaSuccess && !rc) ce = cudaStreamWaitEvent(p->cap, p->ev_g2, 0);
       if (ce != cudaSuccess && !rc) rc = cuda_fail(ce, "step_graph: capture join");
     }
+    kn = g_launches - l0;
+    g_launches = l0;
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(p->cap, &graph);
     if (rc || ce != cudaSuccess || !graph) {
@@ -457,6 +449,7 @@ static int step_graph_impl(onmf_step_plan* p, const onmf_step_buffers* b, const 
   ONMF_CUDA(cudaEventRecord(p->ev_W, main));
   ONMF_CUDA(cudaEventRecord(p->ev_AB, main));
   p->launches += e->kernels;
+  g_launches += e->kernels;
   ++p->graph_steps;
   return ONMF_OK;
 }

@@ -97,7 +97,6 @@ class OnmfEngine:
         self._ev_code = torch.cuda.Event()     # main finished reading W / Xt of the current step
         self._ev_AB = torch.cuda.Event()       # A, B of the previous step blended on side (the next dictionary update follows)
         self._cur = 0
-        self._launches_py = 0
         # fused step (csrc/step.cu): one C call per minibatch enqueues the whole schedule; the Python-composed schedule
         # below (same kernels, same ordering, torch events) remains for analysis (bench.py --timeline)
         self.fused = bool(fused)
@@ -113,12 +112,9 @@ class OnmfEngine:
 
     @property
     def launches(self):
-        """kernels launched so far (Python-composed calls + the fused plan's own count)"""
-        return self._launches_py + (self._plan.launches() if self._plan is not None else 0)
-
-    @launches.setter
-    def launches(self, v):
-        self._launches_py = int(v) - (self._plan.launches() if self._plan is not None else 0)
+        """kernels launched so far by this host thread through libonmf_b200.so (every launch site of the library counts
+        itself; a CUDA-graph replay counts its kernel nodes).  Use differences."""
+        return _lib.launch_count()
 
     def _make_bufs(self):
         """(re)build the onmf_step_buffers descriptor of the fused step from the engine's tensors"""
@@ -207,10 +203,8 @@ class OnmfEngine:
         """Everything the coder needs that depends on the dictionary only: Gram matrix and (tensor-core path)
         the TF32 hi/lo split of W.  Runs right after the dictionary update, off the minibatch's critical path."""
         _lib.gram_f64(W, G, self._ws_gram if use_ws else self._ws_gram_s, stream=stream)
-        self.launches += 2
         if self.use_tc:
             _lib.split_tf32(W, Whi, Wlo, stream=stream)
-            self.launches += 1
 
     def _reserve(self, n):
         if n <= self._cap:
@@ -245,19 +239,12 @@ class OnmfEngine:
     def _stats_ptr(self):
         return self.stats
 
-    def _lars_launches(self):
-        """kernels one onmf_lasso_lars call launches: Gram padding + the tier chain (both first-tier variants when the
-        class has more than one tier) + the scheduling-hint update (csrc/lars.cu launch_class)."""
-        k = self.k
-        return 2 if k <= 32 else 5 if k <= 64 else 6
-
     # ------------------------------------------------------------------ coding only
     def _cov_into(self, Xt, pool, idx, scale, n, W, Whi, Wlo, Ct, stream):
         """Ct = minibatch @ W for a dense minibatch Xt or a minibatch by reference (pool, idx, scale)."""
         if self.fused_tc:
             src = Xt if Xt is not None else pool
             _lib.cov_fused_tc(src, idx if Xt is None else None, n, Whi, Wlo, Ct, scale=scale if Xt is None else 1.0, stream=stream)
-            self.launches += 1
             return
         if Xt is None:
             Xt = self._dense(pool, idx, scale, n, stream)
@@ -265,10 +252,8 @@ class OnmfEngine:
             self._need_split_buffers()
             _lib.split_tf32(Xt, self.Xhi[:n], self.Xlo[:n], stream=stream)
             _lib.cov_tc(self.Xhi[:n], self.Xlo[:n], Whi, Wlo, Ct, stream=stream)
-            self.launches += 2
         else:
             _lib.cov(Xt, W, Ct, stream=stream)
-            self.launches += 1
 
     def _dense(self, pool, idx, scale, n, stream):
         """materialise a minibatch by reference (engines without the fused kernels): K1 gather (+ widening)"""
@@ -279,7 +264,6 @@ class OnmfEngine:
                 self._wide = torch.empty(max(n, 1), self.d, dtype=torch.float32, device=self.device)
             if n:
                 _lib.widen(pool[:n], scale, self._wide[:n], stream=stream)
-                self.launches += 1
             return self._wide[:n]
         if idx is None:
             return pool[:n]
@@ -287,7 +271,6 @@ class OnmfEngine:
             self._Xg = torch.empty(max(n, 1), self.d, dtype=self.dtype, device=self.device)
         if n:
             _lib.gather_rows(pool, idx, self._Xg[:n], stream=stream)
-            self.launches += 1
         return self._Xg[:n]
 
     def sparse_code(self, Xt: torch.Tensor, W: Optional[torch.Tensor] = None, alpha=None, out=None):
@@ -314,7 +297,6 @@ class OnmfEngine:
             self._lars_wide(G, Ct, a, Ht, torch.cuda.current_stream(self.device))
         else:
             _lib.lasso_lars(G, Ct, self.d, a, Ht, self._ws_lars, max_iter=self.max_iter, stats=self._stats_ptr())
-            self.launches += self._lars_launches()
         return Ht
 
     def _lars_wide(self, G64, Ct, alpha, Ht, stream):
@@ -330,7 +312,6 @@ class OnmfEngine:
             _lib.convert(Ht64, Ht, stream=stream)
             for t_ in (Ct64, Ht64, ws):
                 t_.record_stream(stream)
-        self.launches += 2 + self._lars_launches()
 
     # ------------------------------------------------------------------ one online step
     def step_with_codes(self, Xt, Ht, t):
@@ -381,7 +362,6 @@ class OnmfEngine:
                 Ct, Ht = self.Ct[:n], self.Ht[:n]
                 if presplit:
                     _lib.cov_tc(self.Xhi[:n], self.Xlo[:n], self.Whi, self.Wlo, Ct, stream=main)
-                    self.launches += 1
                 else:
                     self._cov_into(Xt, pool, idx, scale, n, self.W, getattr(self, "Whi", None), getattr(self, "Wlo", None), Ct, main)
                 self._lars_wide(self.G, Ct, self.alpha, Ht, main)
@@ -401,7 +381,6 @@ class OnmfEngine:
             _lib.update_dict(self.W, self.A, self.B, self.W_next, stream=side, workspace=self._ws_gram)
             self._derive(self.W_next, self.G_next, getattr(self, "Whi_next", None), getattr(self, "Wlo_next", None), side)
             self._ev_W.record(side)
-            self.launches += 1
         # main stream: code this minibatch with W_{t-1}
         Ht = self.Ht[:n] if codes is None else codes
         if self.track_C:
@@ -411,7 +390,6 @@ class OnmfEngine:
                 Xhi, Xlo = self.Xhi[:n], self.Xlo[:n]
                 if not presplit:
                     _lib.split_tf32(Xt, Xhi, Xlo, stream=main)
-                    self.launches += 1
             if codes is None:
                 Ct = self.Ct[:n]
                 if self.use_tc:
@@ -433,19 +411,15 @@ class OnmfEngine:
                                     stats=self._stats_ptr(), stream=main)
                 finally:
                     _lib.set_option(_lib.OPT_LARS_RESERVED_SMS, saved)
-                self.launches += 1 + self._lars_launches()
             if self.use_tc:
                 _lib.split_tf32(Ht, self.Hhi[:n], self.Hlo[:n], stream=main)
                 _lib.surrogate_partial_tc(self.Hhi[:n], self.Hlo[:n], Xhi, Xlo, self.P[cur], self._ws_sur, stream=main)
-                self.launches += 5            # split + 2 GEMMs + 2 fixed-order reductions
             else:
                 _lib.surrogate_partial(Ht, Xt, self.P[cur], self._ws_sur, stream=main)
-                self.launches += 3            # 2 GEMMs + reduction
             if self.track_C:
                 if presplit:
                     raise _lib.OnmfKernelError("track_C needs the unsplit minibatch")
                 _lib.xxt_partial(Xt, self.P2, self._ws_sur, stream=main)
-                self.launches += 2
         else:
             with torch.cuda.stream(main):
                 self.P[cur].zero_()
@@ -464,11 +438,9 @@ class OnmfEngine:
                 if self.track_C:
                     dist.all_reduce(self.P2, group=self.pg)
             _lib.surrogate_blend(self.P[cur], w, self.A, self.B, stream=side)
-            self.launches += 1
             self._ev_AB.record(side)
             if self.track_C:
                 _lib.axpby(w, self.P2, 1.0 - w, self.C, stream=side)
-                self.launches += 1
         # the next coding needs W_t (= W_next): wait for the dictionary update only
         main.wait_event(self._ev_W)
         self.W, self.W_next = self.W_next, self.W
@@ -587,7 +559,6 @@ class OnmfEngine:
         self.flush()
         out = torch.empty(3, dtype=torch.float64, device=self.device)
         _lib.surrogate_error(self.W, self.G, self.A, self.B, self.C, out)
-        self.launches += 1
         t = out.cpu().tolist()
         return t[0] - 2.0 * t[1] + t[2]
 

@@ -16,7 +16,7 @@ for r in rows[hdr + 1:]:
     ms = v / 1e6 if unit in ("ns", "nsecond") else v / 1e3 if unit in ("us", "usecond") else v
     launches.append((r[ki], ms))
 # a step starts at the gather kernel
-starts = [i for i, (n, _) in enumerate(launches) if "gather_rows_split" in n]
+starts = [i for i, (n, _) in enumerate(launches) if ("gather_rows_split" in n or "cov_fused_kernel" in n)]
 print("%d launches, %d steps" % (len(launches), len(starts)))
 first = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 for s in range(first, len(starts)):
