@@ -13,6 +13,8 @@ build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/onmf_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 
+build/lars.o: $(CSRC)/lars_fast.cuh
+
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 

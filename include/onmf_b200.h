@@ -41,6 +41,8 @@ extern "C" {
 /* options (kept per calling host thread, like the error string) */
 #define ONMF_OPT_LARS_RESERVED_SMS 1  /* SMs the persistent LARS coder leaves free (default 0) so that kernels launched
                                          on other streams (the dictionary update) run concurrently with it */
+#define ONMF_OPT_LARS_FAST_TIER 2     /* 1 (default): the fp32 coder for n_components > 128 walks clean homotopy paths in the
+                                         warp-uniform fast first tier (csrc/lars_fast.cuh); 0: general kernel only */
 int onmf_set_option(int key, int value);
 int onmf_get_option(int key, int* value);
 

@@ -236,6 +236,7 @@ def widen(src, scale, dst, lo=None, stream=None):
 
 
 OPT_LARS_RESERVED_SMS = 1
+OPT_LARS_FAST_TIER = 2
 MAX_COMPONENTS = 512          # largest n_components the LARS coder is instantiated for (csrc/lars.cu k_class)
 
 

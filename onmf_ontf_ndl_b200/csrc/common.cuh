@@ -11,6 +11,7 @@ namespace onmf {
 
 extern thread_local char g_err[512];
 extern thread_local int g_lars_reserved_sms;     // SMs the persistent coder leaves free for concurrently running kernels
+extern thread_local int g_lars_fast;             // 1: the warp-uniform fast first tier of the fp32 coder (k > 128) is used
 extern thread_local long long g_launches;        // kernels launched by this host thread (every launch site counts itself)
 
 inline int fail(int code, const char* msg) {

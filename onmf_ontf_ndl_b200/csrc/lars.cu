@@ -953,6 +953,8 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
   }
 }
 
+#include "lars_fast.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1021,6 +1023,16 @@ static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaSt
     pad_gram_kernel<T><<<cdiv(k * KPAD, 256), 256, 0, st>>>(P.G, P.G64, k, KPAD, const_cast<T*>(P.Gp));
     ONMF_LAUNCH_CHECK("pad_gram_kernel");
     *padded = true;
+  }
+  if constexpr (std::is_same<T, float>::value && LPC == 32 && SPLIT > 0 && !MGLOB) {
+    // fp32 production path, k > 128: the warp-uniform fast tier walks the clean paths and hands everything else on
+    if (!gsm && P.G64 != nullptr && P.ovf_list != nullptr && g_lars_fast) {
+      auto kern = lars_fast_kernel<NA, SMAX, SPLIT>;
+      ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, nw * 32, smem, st>>>(P);
+      ONMF_LAUNCH_CHECK("lars_fast_kernel");
+      return ONMF_OK;
+    }
   }
   if (gsm) {
     auto kern = lars_kernel<T, LPC, NA, SMAX, true, MGLOB, SPLIT>;

@@ -888,3 +888,40 @@ def test_minibatch_by_reference_engine_matches_presplit_engine(monkeypatch, gold
         if fused_tc == "1":
             assert eng.Xhi is None and eng.Hhi is None          # no hi/lo copies of the minibatch or the codes exist
     assert per_atom(outs[0][0], outs[1][0]) < 5e-4 and rel(outs[0][1], outs[1][1]) < 1e-4
+
+
+def test_fast_tier_matches_general_kernel():
+    """csrc/lars_fast.cuh (the warp-uniform first tier of the fp32 coder for k > 128) against the general kernel on the same
+    covariances: learned unit-norm dictionaries (clean paths, <= 64 active atoms), a raw U[0,1) dictionary (most columns
+    outgrow the 64 slots and are handed on), alpha = 0 (long paths, degenerate tails), k < 256 (padded lanes) and the
+    k <= 512 class."""
+    rng = np.random.default_rng(21)
+    def run(G64, Ct, d, alpha, fast):
+        n, k = Ct.shape
+        Ht = torch.full((n, k), float("nan"), device=dev())
+        ws = torch.zeros(_lib.lasso_lars_workspace(torch.float32, k, n), dtype=torch.uint8, device=dev())
+        stats = torch.zeros(8, dtype=torch.int64, device=dev())
+        saved = _lib.get_option(_lib.OPT_LARS_FAST_TIER)
+        _lib.set_option(_lib.OPT_LARS_FAST_TIER, fast)
+        try:
+            _lib.lasso_lars(G64, Ct, d, alpha, Ht, ws, stats=stats)
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_option(_lib.OPT_LARS_FAST_TIER, saved)
+        return Ht, stats.cpu().numpy()
+    assert _lib.get_option(_lib.OPT_LARS_FAST_TIER) == 1                 # the default
+    for (d, k, n, alpha, unit) in [(1024, 256, 3000, 1.0, True), (1024, 256, 300, 1.0, False), (256, 200, 500, 0.0, True),
+                                   (512, 160, 700, 0.3, True), (300, 384, 400, 0.5, True)]:
+        W = rng.random((d, k))
+        if unit:
+            W /= np.linalg.norm(W, axis=0)
+        X = rng.random((n, d))
+        Wt = tt(W, torch.float32)
+        G64 = (Wt.double().T @ Wt.double()).contiguous()
+        G64 = ((G64 + G64.T) / 2).contiguous()
+        Ct = (tt(X, torch.float32) @ Wt).contiguous()
+        H1, s1 = run(G64, Ct, d, alpha, 1)
+        H0, s0 = run(G64, Ct, d, alpha, 0)
+        assert not torch.isnan(H1).any() and not torch.isnan(H0).any()   # every column written by some tier
+        assert s1[0] == n and s0[0] == n, (s1, s0)                       # columns finished
+        assert torch.equal(H1, H0), (d, k, n, alpha, float((H1 - H0).abs().max()), int((H1 != H0).any(1).sum()))
