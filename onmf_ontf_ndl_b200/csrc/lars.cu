@@ -987,6 +987,51 @@ static size_t ovf_scratch_groups(int kp) {
   return g;
 }
 
+// fast first tier: (threads per CTA, columns of V in shared memory, Gram rows in flight) variants
+template <int NA, int SMAX, int SPLIT, int NT, int UQ, bool PF = false>
+static int launch_fast_variant(const LarsParams<float>& P, long long n_upper, cudaStream_t st) {
+  auto kern = lars_fast_kernel<NA, SMAX, SPLIT, NT, UQ, PF>;
+  int nw = NT / 32;
+  const long long per_sm = cdiv<long long>(n_upper, num_sms());          // spread small minibatches over all SMs
+  if (per_sm < nw) nw = per_sm < 1 ? 1 : (int)per_sm;
+  const long long grid_ll = cdiv<long long>(n_upper, nw);
+  int sms = num_sms() - g_lars_reserved_sms;
+  if (sms < 1) sms = 1;
+  const int grid = grid_ll > sms ? sms : (int)grid_ll;
+  const size_t smem = (size_t)nw * fast_group_words<SMAX, SPLIT>() * 4;
+  if ((long)smem > max_smem_optin()) return fail(ONMF_E_UNSUPPORTED, "lasso_lars: fast tier does not fit in shared memory");
+  ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, nw * 32, smem, st>>>(P);
+  ONMF_LAUNCH_CHECK("lars_fast_kernel");
+  return ONMF_OK;
+}
+#ifdef LARS_FAST_EXPERIMENT
+constexpr int FAST_MAX_WARPS = 32, FAST_MIN_SPLIT = 16;
+#else
+constexpr int FAST_MAX_WARPS = 20, FAST_MIN_SPLIT = 32;
+#endif
+template <int NA, int SMAX>
+static int launch_fast(const LarsParams<float>& P, long long n_upper, cudaStream_t st) {
+#ifdef LARS_FAST_EXPERIMENT
+  static int cfg = -1;
+  if (cfg < 0) { const char* e = getenv("ONMF_FAST_CFG"); cfg = e ? atoi(e) : 0; }
+  switch (cfg) {
+    case 1: return launch_fast_variant<NA, SMAX, 32, 640, 4>(P, n_upper, st);
+    case 2: return launch_fast_variant<NA, SMAX, 40, 512, 4, true>(P, n_upper, st);
+    case 3: return launch_fast_variant<NA, SMAX, 32, 640, 4, true>(P, n_upper, st);
+    case 4: return launch_fast_variant<NA, SMAX, 36, 576, 4>(P, n_upper, st);
+    case 5: return launch_fast_variant<NA, SMAX, 28, 704, 4>(P, n_upper, st);
+    case 6: return launch_fast_variant<NA, SMAX, 32, 608, 4>(P, n_upper, st);
+    case 7: return launch_fast_variant<NA, SMAX, 24, 768, 4>(P, n_upper, st);
+    case 8: return launch_fast_variant<NA, SMAX, 32, 704, 4>(P, n_upper, st);
+  }
+#endif
+  // measured at cfg5 (profiles/r2_lars_fast.md): 20 warps x 96 registers with 32 columns of V in shared memory beat 16 x 128 / 40
+  // by 4 %; 16 atoms per lane (k <= 512) do not fit 96 registers
+  if constexpr (NA <= 8) return launch_fast_variant<NA, SMAX, 32, 640, 4>(P, n_upper, st);
+  else return launch_fast_variant<NA, SMAX, 40, 512, 2>(P, n_upper, st);
+}
+
 // *padded: whether the zero-padded global copy of G (P.Gp) has been written in this call; a tier that cannot stage G in
 // shared memory writes it on first need (the small classes in fp32 never do: a launch less on their launch-bound steps)
 template <typename T, int LPC, int NA, int SMAX, bool MGLOB, int SPLIT = 0>
@@ -1026,13 +1071,7 @@ static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaSt
   }
   if constexpr (std::is_same<T, float>::value && LPC == 32 && SPLIT > 0 && !MGLOB) {
     // fp32 production path, k > 128: the warp-uniform fast tier walks the clean paths and hands everything else on
-    if (!gsm && P.G64 != nullptr && P.ovf_list != nullptr && g_lars_fast) {
-      auto kern = lars_fast_kernel<NA, SMAX, SPLIT>;
-      ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<grid, nw * 32, smem, st>>>(P);
-      ONMF_LAUNCH_CHECK("lars_fast_kernel");
-      return ONMF_OK;
-    }
+    if (!gsm && P.G64 != nullptr && P.ovf_list != nullptr && g_lars_fast && k > SMAX) return launch_fast<NA, SMAX>(P, n_upper, st);
   }
   if (gsm) {
     auto kern = lars_kernel<T, LPC, NA, SMAX, true, MGLOB, SPLIT>;
@@ -1058,6 +1097,9 @@ constexpr int HYB_SLOTS = 64, HYB_SPLIT = LARS_HYB_SPLIT;
 static size_t ws_hyb_bytes(int kp) {
   if (kp <= 128) return 0;
   size_t per = (size_t)(HYB_SLOTS * (HYB_SLOTS + 1) / 2 - HYB_SPLIT * (HYB_SPLIT + 1) / 2) * sizeof(double);
+  // (the fast first tier: padded columns, up to FAST_MAX_WARPS warps per SM -- expressed per general-kernel group)
+  const size_t per_fast = (size_t)fast_tail_doubles<HYB_SLOTS, FAST_MIN_SPLIT>() * sizeof(double) * FAST_MAX_WARPS / (LARS_MAX_THREADS / 16) + 8;
+  if (per_fast > per) per = per_fast;
   // resident groups per SM: one per LPC lanes; the k > 128 classes use LPC >= 16
   return round_up<size_t>((size_t)(num_sms() > 160 ? num_sms() : 160) * (LARS_MAX_THREADS / 16) * per, 256);
 }

@@ -25,29 +25,38 @@
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
-template <int NA, int SMAX, int SPLIT>
-__global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsParams<float> P) {
+// Packed storage of the upper-triangular inverse factor V with columns padded to an even number of entries, so that
+// both sweeps read 16-byte pairs: column i holds V[0..i][i] (+ one zero pad entry when i is even) at offset fast_cpad(i).
+__host__ __device__ constexpr int fast_cpad(int i) { return ((i + 1) >> 1) * ((i >> 1) + 1) * 2; }
+// shared-memory words of one warp: V columns 0..SPLIT-1, g and t (FP64), the slot table (atom, weight)
+template <int SMAX, int SPLIT>
+__host__ __device__ constexpr int fast_group_words() { return 2 * fast_cpad(SPLIT) + 4 * SMAX + 2 * SMAX; }
+template <int SMAX, int SPLIT>
+__host__ __device__ constexpr int fast_tail_doubles() { return fast_cpad(SMAX) - fast_cpad(SPLIT); }
+
+template <int NA, int SMAX, int SPLIT, int NT, int UQ, bool PF = false>
+__global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
   typedef float T;
   constexpr int SA = SMAX / 32;          // slot registers per lane (slot p = l + 32 m)
   constexpr int NV = NA / 4;             // float4 loads per Gram row per lane
   constexpr int KP = 32 * NA;            // padded row length of the Gram copy
-  constexpr int UQ = (NA >= 16) ? 2 : 4; // Gram rows in flight per batch of the correlation pass
-  static_assert(SMAX % 32 == 0 && NA % 4 == 0 && SPLIT >= 32 && SPLIT < SMAX, "bad tile shape");
+  static_assert(SMAX % 32 == 0 && NA % 4 == 0 && SPLIT % 2 == 0 && SPLIT < SMAX, "bad tile shape");
 
   if (P.hint != nullptr && *P.hint != (unsigned)P.run_if) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int k = P.k;
-  const int l = threadIdx.x & 31;
+  int l = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  uint32_t* gbase = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * group_words<T, 32, SMAX, false, SPLIT>();
-  constexpr int MELEMS = SMAX * (SMAX + 1) / 2;
-  constexpr int MSM = SPLIT * (SPLIT + 1) / 2;
-  double* Mg = reinterpret_cast<double*>(gbase);                                   // packed columns 0..SPLIT-1 of V
-  double* Mx = P.Mhyb + ((size_t)blockIdx.x * (blockDim.x / 32) + warp) * (size_t)(MELEMS - MSM);   // columns >= SPLIT
-  double* gs = Mg + MSM;                                                           // g = G[A, j]
+  asm volatile("" : "+r"(l));            // (opaque: keeps the lane index in a register instead of re-reading %tid in the loops)
+  uint32_t* gbase = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * fast_group_words<SMAX, SPLIT>();
+  constexpr int MSMP = fast_cpad(SPLIT);                                           // doubles of V kept in shared memory
+  double* Mg = reinterpret_cast<double*>(gbase);                                   // columns 0..SPLIT-1 of V
+  double* Mx = P.Mhyb + ((size_t)blockIdx.x * (blockDim.x / 32) + warp) * (size_t)fast_tail_doubles<SMAX, SPLIT>();   // columns >= SPLIT
+  double* gs = Mg + MSMP;                                                          // g = G[A, j]
   double* us = gs + SMAX;                                                          // t = V^T g
-  SlotW<T>* sw_ = reinterpret_cast<SlotW<T>*>(us + SMAX);                          // (atom, weight) by slot
-  int* acts = reinterpret_cast<int*>(sw_ + SMAX);                                  // slot -> atom
+  SlotW<T>* sw_ = reinterpret_cast<SlotW<T>*>(us + SMAX);                          // (atom, weight) by slot, read in pairs by the correlation pass; free slots (0, 0)
+  // stale entries are read (times an exact zero) by the paired sweeps: they must be finite
+  for (int i = l; i < MSMP + 2 * SMAX; i += 32) Mg[i] = 0.0;
 
   auto atom_of = [&](int m) -> int { return ((m >> 2) * 32 + l) * 4 + (m & 3); };
   unsigned long long Grl = reinterpret_cast<unsigned long long>(P.Gp) + (unsigned long long)l * sizeof(float4);
@@ -61,79 +70,103 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
   const T NINF = -CUDART_INF_F;
   const T BIG = 3.402823466e+38f;
 
-  int ci[SA];
+  int cb[SA];                            // offsets of this lane's own columns
 #pragma unroll
-  for (int m = 0; m < SA; ++m) { const int i = l + 32 * m; ci[m] = i * (i + 1) / 2; }
-  auto Vld = [&](int idx) -> double { return (idx >= MSM) ? Mx[idx - MSM] : Mg[idx]; };
-  auto Vst = [&](int idx, double v) { if (idx >= MSM) Mx[idx - MSM] = v; else Mg[idx] = v; };
+  for (int m = 0; m < SA; ++m) cb[m] = fast_cpad(l + 32 * m);
+  auto Vld = [&](int idx) -> double { return (idx >= MSMP) ? Mx[idx - MSMP] : Mg[idx]; };
+  auto Vst = [&](int idx, double v) { if (idx >= MSMP) Mx[idx - MSMP] = v; else Mg[idx] = v; };
 
-  // t_i = sum_{p <= i} V[p][i] src[p], i < s (this lane's slots)
+  // t_i = sum_{p <= i} V[p][i] src[p] for this lane's columns i < s.  Two rows per step: the column and the source
+  // vector are read as 16-byte pairs (the pad entry of an even column is an exact zero, the source beyond s is finite).
   auto sweep_t = [&](double (&t)[SA], const double* src, int s) {
-    if (s <= 32) {
-      const double* col = Mg + ci[0];
+    const double2* src2 = reinterpret_cast<const double2*>(src);
+    const int np = (s + 1) >> 1;
+    if (s <= 32 && s <= SPLIT) {
+      const double2* col = reinterpret_cast<const double2*>(Mg + cb[0]);
       const int ie = (l < s) ? l : -1;
-#pragma unroll 4
-      for (int p = 0; p < s; ++p) {
-        const double sp = src[p];
-        if (p <= ie) t[0] += col[p] * sp;
+#pragma unroll 2
+      for (int q = 0; q < np; ++q) {
+        const double2 sp = src2[q];
+        if (2 * q <= ie) {
+          const double2 v = col[q];
+          t[0] += v.x * sp.x;
+          t[0] += v.y * sp.y;
+        }
       }
     } else if (s <= SPLIT) {
       int ie[SA];
 #pragma unroll
       for (int m = 0; m < SA; ++m) { const int i = l + 32 * m; ie[m] = (i < s) ? i : -1; }
-#pragma unroll 4
-      for (int p = 0; p < s; ++p) {
-        const double sp = src[p];
+#pragma unroll 2
+      for (int q = 0; q < np; ++q) {
+        const double2 sp = src2[q];
 #pragma unroll
         for (int m = 0; m < SA; ++m)
-          if (p <= ie[m]) t[m] += Mg[ci[m] + p] * sp;
+          if (2 * q <= ie[m]) {
+            const double2 v = reinterpret_cast<const double2*>(Mg + cb[m])[q];
+            t[m] += v.x * sp.x;
+            t[m] += v.y * sp.y;
+          }
       }
     } else {
       int ie[SA];
-      const double* colp[SA];
+      const double2* colp[SA];                   // generic pointers: a lane's column is in shared or in global memory
 #pragma unroll
       for (int m = 0; m < SA; ++m) {
         const int i = l + 32 * m;
         ie[m] = (i < s) ? i : -1;
-        colp[m] = (i >= SPLIT) ? (Mx + (ci[m] - MSM)) : (Mg + ci[m]);
+        colp[m] = reinterpret_cast<const double2*>((cb[m] >= MSMP) ? (Mx + (cb[m] - MSMP)) : (Mg + cb[m]));
       }
 #pragma unroll 2
-      for (int p = 0; p < s; ++p) {
-        const double sp = src[p];
+      for (int q = 0; q < np; ++q) {
+        const double2 sp = src2[q];
 #pragma unroll
         for (int m = 0; m < SA; ++m)
-          if (p <= ie[m]) t[m] += colp[m][p] * sp;
+          if (2 * q <= ie[m]) {
+            const double2 v = colp[m][q];
+            t[m] += v.x * sp.x;
+            t[m] += v.y * sp.y;
+          }
       }
     }
   };
-  // u_p = sum_{p <= i < s} V[p][i] src[i]
+  // u_p = sum_{p <= i < s} V[p][i] src[i].  Two columns per step: the columns i, i + 1 of an even i have the same padded
+  // length i + 2 (row i + 1 of column i is the zero pad; src[s] = 0 when s is odd, the column behind it is finite).
   auto sweep_u = [&](double (&u)[SA], const double* src, int s) {
+    const double2* src2 = reinterpret_cast<const double2*>(src);
     const int nS = s > SPLIT ? SPLIT : s;
-    const double* rp = Mg + l;
     const int nS1 = nS < 32 ? nS : 32;
-#pragma unroll 4
-    for (int i = 0; i < nS1; ++i) {
-      const double si = src[i];
-      if (l <= i) u[0] += rp[0] * si;
-      rp += i + 1;
+    const double* rp = Mg + l;
+    int i = 0;
+#pragma unroll 2
+    for (; i < nS1; i += 2) {
+      const double2 sp = src2[i >> 1];
+      if (l <= i + 1) {
+        u[0] += rp[0] * sp.x;
+        u[0] += rp[i + 2] * sp.y;
+      }
+      rp += 2 * (i + 2);
     }
 #pragma unroll 2
-    for (int i = nS1; i < nS; ++i) {
-      const double si = src[i];
+    for (; i < nS; i += 2) {
+      const double2 sp = src2[i >> 1];
 #pragma unroll
       for (int m = 0; m < SA; ++m)
-        if (l + 32 * m <= i) u[m] += rp[32 * m] * si;
-      rp += i + 1;
+        if (l + 32 * m <= i + 1) {
+          u[m] += rp[32 * m] * sp.x;
+          u[m] += rp[i + 2 + 32 * m] * sp.y;
+        }
+      rp += 2 * (i + 2);
     }
     if (s > SPLIT) {
       rp = Mx + l;
 #pragma unroll 2
-      for (int i = SPLIT; i < s; ++i) {
+      for (i = SPLIT; i < s; ++i) {
         const double si = src[i];
 #pragma unroll
         for (int m = 0; m < SA; ++m)
           if (l + 32 * m <= i) u[m] += rp[32 * m] * si;
-        rp += i + 1;
+        rp += (i + 2) & ~1;
       }
     }
   };
@@ -150,29 +183,32 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
     const long long col = P.col_list ? P.col_list[widx] : (long long)widx;
     const T* crow = P.Ct + (size_t)col * k;
 
-    // active atoms and the padding beyond k carry cov = -inf (see lars_kernel)
-    T cov[NA];
+    // active atoms and the padding beyond k carry cov = -inf (see lars_kernel); pairs of atoms share a 64-bit register pair
+    float2 cov2[NA / 2];
     if (k == KP) {
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         const float4 c4 = *reinterpret_cast<const float4*>(crow + (v * 32 + l) * 4);
-        cov[4 * v + 0] = c4.x; cov[4 * v + 1] = c4.y; cov[4 * v + 2] = c4.z; cov[4 * v + 3] = c4.w;
+        cov2[2 * v] = make_float2(c4.x, c4.y);
+        cov2[2 * v + 1] = make_float2(c4.z, c4.w);
       }
     } else {
 #pragma unroll
-      for (int m = 0; m < NA; ++m) {
+      for (int m = 0; m < NA; m += 2) {
         const int i = atom_of(m);
-        cov[m] = (i < k) ? crow[i] : NINF;
+        cov2[m / 2] = make_float2((i < k) ? crow[i] : NINF, (i + 1 < k) ? crow[i + 1] : NINF);
       }
     }
+    auto covr = [&](int m) -> T& { return (m & 1) ? cov2[m >> 1].y : cov2[m >> 1].x; };
+    // per-slot state lives in the registers of the slot's lane (slot p = l + 32 m): atom, coefficient, weights
     T coef[SA], prev[SA];
     double wd[SA];
+    int a_reg[SA];
 #pragma unroll
     for (int m = 0; m < SA; ++m) {
-      coef[m] = T(0); prev[m] = T(0); wd[m] = 0.0;
+      coef[m] = T(0); prev[m] = T(0); wd[m] = 0.0; a_reg[m] = 0;
       SlotW<T> z; z.atom = 0; z.w = T(0);
       sw_[l + 32 * m] = z;
-      acts[l + 32 * m] = -1;
     }
     double sw = 0.0;
     int n_iter = 0, n_act = 0, max_act = 0;
@@ -191,12 +227,12 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
       // ---- 1. largest inactive covariance (value first, then the lowest atom attaining it) ----
       T best = NINF;
 #pragma unroll
-      for (int m = 0; m < NA; ++m) best = cov[m] > best ? cov[m] : best;
+      for (int m = 0; m < NA; ++m) best = fmaxf(best, covr(m));
       best = gmaxval<32>(best, 0xffffffffu);
       int bi = 0x7fffffff;
 #pragma unroll
       for (int m = NA - 1; m >= 0; --m)
-        if (cov[m] == best) bi = atom_of(m);
+        if (covr(m) == best) bi = atom_of(m);
       bi = __reduce_min_sync(0xffffffffu, bi);
       if (UNI(banned >= 0)) {
         // the atom dropped by the last drop step cannot be the joiner of the first join knot after it (see lars_kernel)
@@ -205,13 +241,13 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
           int i2 = 0x7fffffff;
 #pragma unroll
           for (int m = 0; m < NA; ++m) {
-            const T cv = (atom_of(m) == banned) ? NINF : cov[m];
+            const T cv = (atom_of(m) == banned) ? NINF : covr(m);
             b2 = cv > b2 ? cv : b2;
           }
           b2 = gmaxval<32>(b2, 0xffffffffu);
 #pragma unroll
           for (int m = NA - 1; m >= 0; --m)
-            if (cov[m] == b2 && atom_of(m) != banned) i2 = atom_of(m);
+            if (covr(m) == b2 && atom_of(m) != banned) i2 = atom_of(m);
           i2 = __reduce_min_sync(0xffffffffu, i2);
           if (b2 > NINF) { best = b2; bi = i2; }
         }
@@ -229,14 +265,15 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
         }
         break;
       }
-      if (UNI(n_iter >= P.max_iter || n_act >= k)) { handoff = true; break; }
+      if (UNI(n_iter >= P.max_iter)) { handoff = true; break; }
 
       // ---- 2. atom j joins slot n_act ----
       if (UNI(!drop)) {
         if (UNI(n_act >= SMAX)) { handoff = true; slots_full = true; break; }
         const int j = bi;
         const int s = n_act;
-        const double gjj = G64[(size_t)j * k + j];
+        const double* __restrict__ g64row = G64 + (size_t)j * k;      // row j of the (bitwise symmetric) FP64 Gram
+        const double gjj = g64row[j];
         double t[SA], u[SA];
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
@@ -244,7 +281,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
           if (32 * m < s) {
             const int p = l + 32 * m;
             double gv = 0.0;
-            if (p < s) gv = G64[(size_t)j * k + acts[p]];
+            if (p < s) gv = g64row[a_reg[m]];
             gs[p] = gv;
           }
         }
@@ -254,7 +291,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
           tt += t[m] * t[m];
-          if (32 * m < s) us[l + 32 * m] = t[m];
+          if (32 * m < s) us[l + 32 * m] = t[m];      // (zero beyond s: the paired sweep reads us[s] when s is odd)
         }
         __syncwarp();
         sweep_u(u, us, s);
@@ -274,18 +311,18 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
         if (UNI(asig < 1e-14)) { handoff = true; break; }          // degenerate regressor: the general kernel handles it
 #pragma unroll
         for (int m = 0; m < NA; ++m)
-          if (atom_of(m) == j) cov[m] = NINF;
+          if (atom_of(m) == j) covr(m) = NINF;
         const double rs = fast_rsqrt(asig);
         const double tau = (1.0 - su) * rs * rs;
-        const int cs = s * (s + 1) / 2;
+        const int cs = fast_cpad(s);
+        const int top = s | 1;                         // an even column carries one zero pad entry
+        double* vcol = (s < SPLIT) ? (Mg + cs) : (Mx + (cs - MSMP));
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
           const int p = l + 32 * m;
-          if (p <= s) {
-            Vst(cs + p, (p == s) ? rs : -u[m] * rs);
-            wd[m] = (p == s) ? tau : wd[m] - tau * u[m];
-            if (p == s) acts[p] = j;
-          }
+          if (p <= top) vcol[p] = (p < s) ? -u[m] * rs : (p == s ? rs : 0.0);
+          if (p <= s) wd[m] = (p == s) ? tau : wd[m] - tau * u[m];
+          if (p == s) { a_reg[m] = j; sw_[p].atom = j; }
         }
         sw += tau * (1.0 - su);
         n_act = s + 1;
@@ -293,43 +330,43 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
         __syncwarp();
       }
 
-      // the Gram rows of the first batch belong to slots 0..UQ-1, final once the join is done: request them now
+      // the Gram rows of the first batch belong to slots 0..UQ-1, final once the join is done: request them now.  Only the
+      // rows of occupied slots are loaded (the L1 data pipe is what this kernel is bound by); the others read as zeros.
       float4 gv0[UQ][NV];
 #pragma unroll
       for (int t = 0; t < UQ; ++t) {
-        const int a0 = acts[t];
-        const float4* row = reinterpret_cast<const float4*>(Grl + (unsigned long long)(unsigned)(a0 >= 0 ? a0 : 0) * (unsigned)(KP * sizeof(T)));
+        const float4* row = reinterpret_cast<const float4*>(Grl + (unsigned long long)(unsigned)sw_[t].atom * (unsigned)(KP * sizeof(T)));
 #pragma unroll
-        for (int v = 0; v < NV; ++v) gv0[t][v] = ld_global_vec(row + v * 32);
+        for (int v = 0; v < NV; ++v) gv0[t][v] = (t < n_act) ? ld_global_vec(row + v * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      // ---- 3. "alpha increasing" (sklearn _least_angle.py:752-765), singular block: general kernel ----
-      if (UNI((n_iter > 0 && a_prev < C) || !(sw > 0.0 && sw < 1e300))) { handoff = true; break; }
-
-      // ---- 4. normalise the equiangular weights ----
+      // ---- 3. normalise the equiangular weights ----
       const double AAd = fast_rsqrt1(sw);
       const T AA = (T)AAd;
+      // "alpha increasing" (sklearn _least_angle.py:752-765) or a numerically singular active block (1^T G_AA^-1 1 not
+      // positive and finite: AA is then NaN, inf or 0): the general kernel decides
+      if (UNI((n_iter > 0 && a_prev < C) || !(AA > T(0) && AA < BIG))) { handoff = true; break; }
       T w[SA];
 #pragma unroll
       for (int m = 0; m < SA; ++m) {
         w[m] = (T)(wd[m] * AAd);
         if (32 * m < n_act) {
           const int p = l + 32 * m;
-          if (p < n_act) {
-            SlotW<T> e; e.atom = acts[p]; e.w = w[m];
-            sw_[p] = e;
-          }
+          if (p < n_act) sw_[p].w = w[m];
         }
       }
       __syncwarp();
 
-      // ---- 5. correlation of every atom with the equiangular direction ----
+      // ---- 4. correlation of every atom with the equiangular direction: rows of the active atoms, slot order ----
       float2 corr2[NA / 2];
 #pragma unroll
       for (int m = 0; m < NA / 2; ++m) corr2[m] = make_float2(0.f, 0.f);
       {
         SlotW<T> e[UQ];
 #pragma unroll
-        for (int t = 0; t < UQ; ++t) e[t] = sw_[t];
+        for (int t = 0; t < UQ; t += 2) {
+          const float4 e2 = *reinterpret_cast<const float4*>(sw_ + t);          // two slot entries per load
+          e[t].w = e2.y; e[t + 1].w = e2.w;
+        }
 #pragma unroll
         for (int t = 0; t < UQ; ++t) {
           const float2 ww = make_float2(e[t].w, e[t].w);
@@ -341,15 +378,25 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
         }
       }
       for (int q0 = UQ; q0 < n_act; q0 += UQ) {
+        const int nr = n_act - q0;
+        if (PF && NV * UQ * 4 == 32 && q0 + UQ < n_act) {
+          // the next batch's rows into L1 while this batch is used: lane l takes line (l % (4 NV)) of row (l / (4 NV))
+          const int pa = sw_[q0 + UQ + l / (4 * NV)].atom;
+          const char* pl = reinterpret_cast<const char*>(P.Gp) + (size_t)pa * (KP * sizeof(T)) + (l % (4 * NV)) * 128;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pl));
+        }
         SlotW<T> e[UQ];
 #pragma unroll
-        for (int t = 0; t < UQ; ++t) e[t] = sw_[q0 + t];
+        for (int t = 0; t < UQ; t += 2) {
+          const float4 e2 = *reinterpret_cast<const float4*>(sw_ + q0 + t);
+          e[t].atom = __float_as_int(e2.x); e[t].w = e2.y; e[t + 1].atom = __float_as_int(e2.z); e[t + 1].w = e2.w;
+        }
         float4 gv[UQ][NV];
 #pragma unroll
         for (int t = 0; t < UQ; ++t) {
           const float4* row = reinterpret_cast<const float4*>(Grl + (unsigned long long)(unsigned)e[t].atom * (unsigned)(KP * sizeof(T)));
 #pragma unroll
-          for (int v = 0; v < NV; ++v) gv[t][v] = ld_global_vec(row + v * 32);
+          for (int v = 0; v < NV; ++v) gv[t][v] = (t < nr) ? ld_global_vec(row + v * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int t = 0; t < UQ; ++t) {
@@ -361,20 +408,28 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
           }
         }
       }
-      T corr[NA];
-#pragma unroll
-      for (int m = 0; m < NA / 2; ++m) { corr[2 * m] = corr2[m].x; corr[2 * m + 1] = corr2[m].y; }
 
-      // ---- 6. step length ----
-      T g1 = BIG;
+      // ---- 5. step length: min over the candidates v = max(C - cov, 0) / (AA - corr + tiny) with a positive denominator.
+      // v >= +0 exactly when the denominator is positive (the numerator is >= +0), and the bit patterns of non-negative
+      // floats order like unsigned integers (negative values, -0 and NaN sort above every positive finite one), so the
+      // test "den > 0 and v < g1" of the general kernel is one unsigned minimum ----
+      unsigned g1u = __float_as_uint(BIG);
+      {
+        const float2 mone = make_float2(-1.f, -1.f), AA2 = make_float2(AA, AA), C2 = make_float2(C, C), tiny2 = make_float2(tiny, tiny);
 #pragma unroll
-      for (int m = 0; m < NA; ++m) {
-        const T den = AA - corr[m] + tiny;
-        const T num = C - cov[m];
-        const T v = qdiv(num > T(0) ? num : T(0), den);
-        if (den > T(0) && v < g1) g1 = v;
+        for (int m = 0; m < NA / 2; ++m) {
+          const float2 den = __fadd2_rn(ffma2(corr2[m], mone, AA2), tiny2);
+          float2 num = ffma2(cov2[m], mone, C2);
+          num.x = fmaxf(num.x, 0.f);
+          num.y = fmaxf(num.y, 0.f);
+          float2 r;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(den.x));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(den.y));
+          const float2 v = __fmul2_rn(num, r);
+          g1u = min(g1u, min(__float_as_uint(v.x), __float_as_uint(v.y)));
+        }
       }
-      g1 = gminpos<32>(g1, 0xffffffffu);
+      const T g1 = __uint_as_float(__reduce_min_sync(0xffffffffu, g1u));
       T gamma = qdiv(C, AA);
       gamma = g1 < gamma ? g1 : gamma;
       T zbest = BIG;
@@ -392,7 +447,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
       gargminpos<32>(zbest, zs, 0xffffffffu);
       drop = UNI(zbest < gamma && zs >= 0);
       if (drop) { gamma = zbest; dslot = zs; }
-      // ---- 7. move along the path ----
+      // ---- 6. move along the path ----
       ++n_iter;
       a_prev = C;
       ghost_atom = -1;
@@ -401,15 +456,23 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
         prev[m] = coef[m];
         coef[m] = prev[m] + gamma * w[m];
       }
+      {
+        const float2 mg = make_float2(-gamma, -gamma);
 #pragma unroll
-      for (int m = 0; m < NA; ++m) cov[m] -= gamma * corr[m];
+        for (int m = 0; m < NA / 2; ++m) cov2[m] = ffma2(corr2[m], mg, cov2[m]);
+      }
       kn_s += (unsigned)n_act;
       kn_s2 += (unsigned)(n_act * n_act);
 
-      // ---- 8. atom leaves slot p0 (Givens downdate of the factor; see lars_kernel) ----
+      // ---- 7. atom leaves slot p0 (Givens downdate of the factor; see lars_kernel) ----
       if (drop) {
         const int p0 = dslot;
-        const int a_d = acts[dslot];
+        int a_d = 0;
+#pragma unroll
+        for (int m = 0; m < SA; ++m) {
+          const int v = __shfl_sync(0xffffffffu, a_reg[m], dslot & 31);
+          if ((dslot >> 5) == m) a_d = v;
+        }
         const int sD = n_act;
         double rr[SA], mv[SA], pre[SA];
         T gp = T(0);
@@ -417,7 +480,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
           const int i = l + 32 * m;
-          rr[m] = (i >= p0 && i < n_act) ? Vld(ci[m] + p0) : 0.0;
+          rr[m] = (i >= p0 && i < n_act) ? Vld(cb[m] + p0) : 0.0;
           mv[m] = 0.0;
           if (32 * m < sD) us[i] = rr[m];
           if (i == p0) { gp = prev[m]; wp0 = wd[m]; rp0 = rr[m]; }
@@ -470,16 +533,17 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
         {
           double R[SA];
           int nrow[SA];
+          const int c0 = fast_cpad(p0);
 #pragma unroll
           for (int m = 0; m < SA; ++m) {
             const int p = l + 32 * m;
-            R[m] = (p <= p0) ? Vld(p0 * (p0 + 1) / 2 + p) : 0.0;
+            R[m] = (p <= p0) ? Vld(c0 + p) : 0.0;
             nrow[m] = (p < p0) ? p : (p == p0 ? -1 : p - 1);
           }
           __syncwarp();
           for (int i = p0; i + 1 < sD; ++i) {
             const double c = gs[i + 1], sn = us[i + 1];
-            const int cn = (i + 1) * (i + 2) / 2, co = i * (i + 1) / 2;
+            const int cn = fast_cpad(i + 1), co = fast_cpad(i);
 #pragma unroll
             for (int m = 0; m < SA; ++m) {
               if (32 * m <= i + 1) {
@@ -488,45 +552,46 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
                   const double X = Vld(cn + p);
                   const double nc = c * R[m] + sn * X;
                   R[m] = c * X - sn * R[m];
-                  if (nrow[m] >= 0) Vst(co + nrow[m], nc);
+                  if (nrow[m] >= 0) Vst(co + nrow[m], nc);   // (rows 0..i of the new column i; its pad entry stays zero)
                 }
               }
             }
             __syncwarp();
           }
         }
-        int nxt_act[SA];
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
           const int p = l + 32 * m;
-          nxt_act[m] = (p + 1 < SMAX) ? acts[p + 1] : -1;
           wd[m] = (p < n_act && p != p0) ? wd[m] - fw * mv[m] : 0.0;
         }
+        // close the gap: slot p + 1 -> slot p for p >= p0 (the freed last slot ends up with zeros)
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
           const int p = l + 32 * m;
           const T c_dn = __shfl_down_sync(0xffffffffu, coef[m], 1, 32);
           const T p_dn = __shfl_down_sync(0xffffffffu, prev[m], 1, 32);
           const double w_dn = __shfl_down_sync(0xffffffffu, wd[m], 1, 32);
+          const int a_dn = __shfl_down_sync(0xffffffffu, a_reg[m], 1, 32);
           const T c_wr = __shfl_sync(0xffffffffu, (m + 1 < SA) ? coef[m + 1 < SA ? m + 1 : m] : T(0), 0, 32);
           const T p_wr = __shfl_sync(0xffffffffu, (m + 1 < SA) ? prev[m + 1 < SA ? m + 1 : m] : T(0), 0, 32);
           const double w_wr = __shfl_sync(0xffffffffu, (m + 1 < SA) ? wd[m + 1 < SA ? m + 1 : m] : 0.0, 0, 32);
+          const int a_wr = __shfl_sync(0xffffffffu, (m + 1 < SA) ? a_reg[m + 1 < SA ? m + 1 : m] : 0, 0, 32);
           if (p >= p0) {
             coef[m] = (l == 31) ? c_wr : c_dn;
             prev[m] = (l == 31) ? p_wr : p_dn;
             wd[m] = (l == 31) ? w_wr : w_dn;
+            a_reg[m] = (l == 31) ? a_wr : a_dn;
           }
         }
-        __syncwarp();
+        --n_act;
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
           const int p = l + 32 * m;
-          if (p >= p0) acts[p] = nxt_act[m];
+          if (p >= n_act) a_reg[m] = 0;
+          if (p >= p0 && p <= n_act) { SlotW<T> e; e.atom = a_reg[m]; e.w = T(0); sw_[p] = e; }     // slot n_act: free again
         }
         sw = sw - wp0 - fw * (sum_m - mpp);
-        --n_act;
         ++st_drops;
-        if (l == 0) { SlotW<T> z; z.atom = 0; z.w = T(0); sw_[n_act] = z; }
         __syncwarp();
         // exact covariance of the dropped atom (sklearn _least_angle.py:891)
         T part = T(0);
@@ -535,14 +600,14 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
         for (int m = 0; m < SA; ++m) {
           if (32 * m < n_act) {
             const int p = l + 32 * m;
-            if (p < n_act) part += grow[acts[p]] * coef[m];
+            if (p < n_act) part += grow[a_reg[m]] * coef[m];
           }
         }
         part = gsum<32>(part);
         const T cnew = crow[a_d] - part;
 #pragma unroll
         for (int m = 0; m < NA; ++m)
-          if (atom_of(m) == a_d) cov[m] = cnew;
+          if (atom_of(m) == a_d) covr(m) = cnew;
         __syncwarp();
       }
     }  // path loop
@@ -564,7 +629,7 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_fast_kernel(LarsPara
 #pragma unroll
       for (int m = 0; m < SA; ++m) {
         const int p = l + 32 * m;
-        if (p < n_act) hrow[acts[p]] = coef[m];
+        if (p < n_act) hrow[a_reg[m]] = coef[m];
       }
       if (l == 0 && ghost_atom >= 0 && ghost_val != T(0)) hrow[ghost_atom] = ghost_val;
       if (l == 0) {
