@@ -42,7 +42,7 @@ WORKLOADS = {
 }
 METRIC = "ONMF samples/sec (code+surrogate+dict update)"
 UNIT = "samples/s"
-LARS_DRAM_BYTES = 4.93e8     # ncu dram bytes of one first-tier coder launch at cfg5, N=1 (profiles/r1_lars_k256_ncu.md)
+LARS_DRAM_BYTES = 4.92e8     # ncu dram bytes of one first-tier coder launch at cfg5, N=1 (profiles/r2_lars_fast.md)
 
 
 def workload_name(name, d, k, n_global, alpha):
@@ -454,7 +454,16 @@ def run_ours(args):
     # knot with active size s: one k x s correlation pass = 2ks flop, FP64 factor sweeps = 3 s^2 flop) / launch time;
     # `peak` = 148 SMs x 128 FMA lanes x 2 at the SM clock observed during the timed region.  The HBM and
     # shared-memory views are kept beside it.
-    roofline = {"bound": "fp32_fma", "kernel": "lars_kernel (K3 sparse coder)", "achieved": fp32_ach, "peak": fp32_peak,
+    # What the profiler shows to be the binding unit (profiles/r2_lars_fast.md) is the L1 data pipe: the Gram rows of the
+    # correlation pass (4ks bytes per knot, the algorithmic minimum of a path-following coder), the FP64 factor sweeps,
+    # gathers and shuffles all pass through it; ncu: 78 % of its peak in every version of the kernel.  `l1_data_pipe`
+    # reports the algorithmic part (Gram-row bytes only) live, the profiler's total utilisation as the recorded constant.
+    gram_bytes = 4.0 * k * stats["sum_active"]
+    l1_pipe = {"algorithmic_gram_row_gbs": gram_bytes / lars_total_s / 1e9, "peak_gbs_at_clock": smem_peak,
+               "frac_algorithmic": gram_bytes / lars_total_s / 1e9 / smem_peak,
+               "ncu_total_utilisation": 0.78 if (args.workload == "cfg5" and not args.batch) else None,
+               "source": "profiles/r2_lars_fast.md (l1tex__data_pipe_lsu_wavefronts, pct of peak)"}
+    roofline = {"bound": "fp32_fma", "kernel": "lars_fast_kernel / lars_kernel (K3 sparse coder)", "achieved": fp32_ach, "peak": fp32_peak,
                 "unit": "TFLOP/s", "frac": fp32_ach / fp32_peak,
                 "peak_source": "148 SMs x 128 lanes x 2 flop x observed SM clock (%.0f MHz)" % (sm_clock / 1e6),
                 # dram__bytes_read.sum + dram__bytes_write.sum of one first-tier launch at cfg5, N=1 (ncu --set full,
@@ -464,6 +473,7 @@ def run_ours(args):
                 "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": achieved, "peak_gbs": hbm_peak,
                         "frac": achieved / hbm_peak, "peak_source": peak_src},
                 "smem": {"achieved_gbs": smem_ach, "peak_gbs_at_clock": smem_peak, "frac": smem_ach / smem_peak},
+                "l1_data_pipe": l1_pipe,
                 "work": {"knots_per_column": stats["knots"] / cols, "mean_active": stats["sum_active"] / max(stats["knots"], 1),
                          "max_active": stats["max_active"], "drops_per_column": stats["drops"] / cols,
                          "overflow_columns": stats["overflow"], "flagged_columns": stats["flagged"],

@@ -988,9 +988,9 @@ static size_t ovf_scratch_groups(int kp) {
 }
 
 // fast first tier: (threads per CTA, columns of V in shared memory, Gram rows in flight) variants
-template <int NA, int SMAX, int SPLIT, int NT, int UQ, bool PF = false>
+template <int NA, int SMAX, int SPLIT, int NT, int UQ, int LW = 4, bool NOAL = false>
 static int launch_fast_variant(const LarsParams<float>& P, long long n_upper, cudaStream_t st) {
-  auto kern = lars_fast_kernel<NA, SMAX, SPLIT, NT, UQ, PF>;
+  auto kern = lars_fast_kernel<NA, SMAX, SPLIT, NT, UQ, LW, NOAL>;
   int nw = NT / 32;
   const long long per_sm = cdiv<long long>(n_upper, num_sms());          // spread small minibatches over all SMs
   if (per_sm < nw) nw = per_sm < 1 ? 1 : (int)per_sm;
@@ -1008,7 +1008,7 @@ static int launch_fast_variant(const LarsParams<float>& P, long long n_upper, cu
 #ifdef LARS_FAST_EXPERIMENT
 constexpr int FAST_MAX_WARPS = 32, FAST_MIN_SPLIT = 16;
 #else
-constexpr int FAST_MAX_WARPS = 20, FAST_MIN_SPLIT = 32;
+constexpr int FAST_MAX_WARPS = 20, FAST_MIN_SPLIT = 28;
 #endif
 template <int NA, int SMAX>
 static int launch_fast(const LarsParams<float>& P, long long n_upper, cudaStream_t st) {
@@ -1016,20 +1016,19 @@ static int launch_fast(const LarsParams<float>& P, long long n_upper, cudaStream
   static int cfg = -1;
   if (cfg < 0) { const char* e = getenv("ONMF_FAST_CFG"); cfg = e ? atoi(e) : 0; }
   switch (cfg) {
-    case 1: return launch_fast_variant<NA, SMAX, 32, 640, 4>(P, n_upper, st);
-    case 2: return launch_fast_variant<NA, SMAX, 40, 512, 4, true>(P, n_upper, st);
-    case 3: return launch_fast_variant<NA, SMAX, 32, 640, 4, true>(P, n_upper, st);
-    case 4: return launch_fast_variant<NA, SMAX, 36, 576, 4>(P, n_upper, st);
-    case 5: return launch_fast_variant<NA, SMAX, 28, 704, 4>(P, n_upper, st);
-    case 6: return launch_fast_variant<NA, SMAX, 32, 608, 4>(P, n_upper, st);
-    case 7: return launch_fast_variant<NA, SMAX, 24, 768, 4>(P, n_upper, st);
-    case 8: return launch_fast_variant<NA, SMAX, 32, 704, 4>(P, n_upper, st);
+    case 1: return launch_fast_variant<NA, SMAX, 32, 640, 4, 4, false>(P, n_upper, st);
+    case 2: return launch_fast_variant<NA, SMAX, 28, 640, 4, 4, true>(P, n_upper, st);
+    case 3: return launch_fast_variant<NA, SMAX, 28, 640, 4, 2, true>(P, n_upper, st);
+    case 4: return launch_fast_variant<NA, SMAX, 32, 640, 4, 2, false>(P, n_upper, st);
+    case 5: return launch_fast_variant<NA, SMAX, 40, 512, 4, 2, true>(P, n_upper, st);
+    case 6: return launch_fast_variant<NA, SMAX, 28, 640, 2, 2, true>(P, n_upper, st);
   }
 #endif
-  // measured at cfg5 (profiles/r2_lars_fast.md): 20 warps x 96 registers with 32 columns of V in shared memory beat 16 x 128 / 40
-  // by 4 %; 16 atoms per lane (k <= 512) do not fit 96 registers
-  if constexpr (NA <= 8) return launch_fast_variant<NA, SMAX, 32, 640, 4>(P, n_upper, st);
-  else return launch_fast_variant<NA, SMAX, 40, 512, 2>(P, n_upper, st);
+  // measured at cfg5 (profiles/r2_lars_fast.md): 20 warps x 96 registers with 28 columns of V in shared memory (98 KB per CTA,
+  // which leaves the larger L1 carve-out to the Gram rows) beat 16 warps x 128 registers / 40 columns by 5 %; 16 atoms per
+  // lane (k <= 512) do not fit 96 registers
+  if constexpr (NA <= 8) return launch_fast_variant<NA, SMAX, 28, 640, 4, 4, true>(P, n_upper, st);
+  else return launch_fast_variant<NA, SMAX, 40, 512, 2, 4, true>(P, n_upper, st);
 }
 
 // *padded: whether the zero-padded global copy of G (P.Gp) has been written in this call; a tier that cannot stage G in

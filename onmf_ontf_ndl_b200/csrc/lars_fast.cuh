@@ -24,6 +24,39 @@
 #define UNI(cond) __any_sync(0xffffffffu, (cond))
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+// loads / stores that leave L1 to the Gram rows: the FP64 Gram entries of a join (a 2 KB row touched once) and the
+// streamed covariance / code rows do not allocate there
+template <bool NA_>
+__device__ __forceinline__ double ld_f64_stream(const double* p) {
+  if (!NA_) return *p;
+  double v;
+  asm("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+template <bool NA_>
+__device__ __forceinline__ float2 ld_f32x2_stream(const float2* p) {
+  if (!NA_) return *p;
+  float2 v;
+  asm("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ld_global_vec(const float2* p) {
+  float2 v;
+  asm("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+// one lane's piece of a Gram row per load: LW consecutive atoms (a warp-wide load covers 32 LW atoms = LW / 32 KB)
+template <int LW> struct RowVec;
+template <> struct RowVec<4> { typedef float4 type; };
+template <> struct RowVec<2> { typedef float2 type; };
+__device__ __forceinline__ void row_zero(float4& v) { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void row_zero(float2& v) { v = make_float2(0.f, 0.f); }
+// corr[pairs of this vector] += g * w
+__device__ __forceinline__ void row_fma(float2* c2, const float4& g, const float2& ww) {
+  c2[0] = ffma2(make_float2(g.x, g.y), ww, c2[0]);
+  c2[1] = ffma2(make_float2(g.z, g.w), ww, c2[1]);
+}
+__device__ __forceinline__ void row_fma(float2* c2, const float2& g, const float2& ww) { c2[0] = ffma2(g, ww, c2[0]); }
 
 // Packed storage of the upper-triangular inverse factor V with columns padded to an even number of entries, so that
 // both sweeps read 16-byte pairs: column i holds V[0..i][i] (+ one zero pad entry when i is even) at offset fast_cpad(i).
@@ -34,11 +67,13 @@ __host__ __device__ constexpr int fast_group_words() { return 2 * fast_cpad(SPLI
 template <int SMAX, int SPLIT>
 __host__ __device__ constexpr int fast_tail_doubles() { return fast_cpad(SMAX) - fast_cpad(SPLIT); }
 
-template <int NA, int SMAX, int SPLIT, int NT, int UQ, bool PF = false>
+template <int NA, int SMAX, int SPLIT, int NT, int UQ, int LW = 4, bool NOAL = false>
 __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
   typedef float T;
   constexpr int SA = SMAX / 32;          // slot registers per lane (slot p = l + 32 m)
-  constexpr int NV = NA / 4;             // float4 loads per Gram row per lane
+  typedef typename RowVec<LW>::type RowV;
+  constexpr int NV = NA / LW;            // loads per Gram row per lane
+  constexpr int PV = LW / 2;             // atom pairs per load
   constexpr int KP = 32 * NA;            // padded row length of the Gram copy
   static_assert(SMAX % 32 == 0 && NA % 4 == 0 && SPLIT % 2 == 0 && SPLIT < SMAX, "bad tile shape");
 
@@ -58,8 +93,8 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
   // stale entries are read (times an exact zero) by the paired sweeps: they must be finite
   for (int i = l; i < MSMP + 2 * SMAX; i += 32) Mg[i] = 0.0;
 
-  auto atom_of = [&](int m) -> int { return ((m >> 2) * 32 + l) * 4 + (m & 3); };
-  unsigned long long Grl = reinterpret_cast<unsigned long long>(P.Gp) + (unsigned long long)l * sizeof(float4);
+  auto atom_of = [&](int m) -> int { return ((m / LW) * 32 + l) * LW + (m % LW); };
+  unsigned long long Grl = reinterpret_cast<unsigned long long>(P.Gp) + (unsigned long long)l * sizeof(RowV);
   asm volatile("" : "+l"(Grl));
   const double* __restrict__ G64 = P.G64;
 
@@ -187,11 +222,8 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
     float2 cov2[NA / 2];
     if (k == KP) {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const float4 c4 = *reinterpret_cast<const float4*>(crow + (v * 32 + l) * 4);
-        cov2[2 * v] = make_float2(c4.x, c4.y);
-        cov2[2 * v + 1] = make_float2(c4.z, c4.w);
-      }
+      for (int v = 0; v < NA / 2; ++v)
+        cov2[v] = ld_f32x2_stream<NOAL>(reinterpret_cast<const float2*>(crow + ((v / PV) * 32 + l) * LW + (v % PV) * 2));
     } else {
 #pragma unroll
       for (int m = 0; m < NA; m += 2) {
@@ -273,7 +305,7 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
         const int j = bi;
         const int s = n_act;
         const double* __restrict__ g64row = G64 + (size_t)j * k;      // row j of the (bitwise symmetric) FP64 Gram
-        const double gjj = g64row[j];
+        const double gjj = ld_f64_stream<NOAL>(g64row + j);
         double t[SA], u[SA];
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
@@ -281,7 +313,7 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
           if (32 * m < s) {
             const int p = l + 32 * m;
             double gv = 0.0;
-            if (p < s) gv = g64row[a_reg[m]];
+            if (p < s) gv = ld_f64_stream<NOAL>(g64row + a_reg[m]);
             gs[p] = gv;
           }
         }
@@ -332,12 +364,15 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
 
       // the Gram rows of the first batch belong to slots 0..UQ-1, final once the join is done: request them now.  Only the
       // rows of occupied slots are loaded (the L1 data pipe is what this kernel is bound by); the others read as zeros.
-      float4 gv0[UQ][NV];
+      RowV gv0[UQ][NV];
 #pragma unroll
       for (int t = 0; t < UQ; ++t) {
-        const float4* row = reinterpret_cast<const float4*>(Grl + (unsigned long long)(unsigned)sw_[t].atom * (unsigned)(KP * sizeof(T)));
+        const RowV* row = reinterpret_cast<const RowV*>(Grl + (unsigned long long)(unsigned)sw_[t].atom * (unsigned)(KP * sizeof(T)));
 #pragma unroll
-        for (int v = 0; v < NV; ++v) gv0[t][v] = (t < n_act) ? ld_global_vec(row + v * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int v = 0; v < NV; ++v) {
+          if (t < n_act) gv0[t][v] = ld_global_vec(row + v * 32);
+          else row_zero(gv0[t][v]);
+        }
       }
       // ---- 3. normalise the equiangular weights ----
       const double AAd = fast_rsqrt1(sw);
@@ -371,41 +406,32 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
         for (int t = 0; t < UQ; ++t) {
           const float2 ww = make_float2(e[t].w, e[t].w);
 #pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            corr2[2 * v] = ffma2(make_float2(gv0[t][v].x, gv0[t][v].y), ww, corr2[2 * v]);
-            corr2[2 * v + 1] = ffma2(make_float2(gv0[t][v].z, gv0[t][v].w), ww, corr2[2 * v + 1]);
-          }
+          for (int v = 0; v < NV; ++v) row_fma(&corr2[PV * v], gv0[t][v], ww);
         }
       }
       for (int q0 = UQ; q0 < n_act; q0 += UQ) {
         const int nr = n_act - q0;
-        if (PF && NV * UQ * 4 == 32 && q0 + UQ < n_act) {
-          // the next batch's rows into L1 while this batch is used: lane l takes line (l % (4 NV)) of row (l / (4 NV))
-          const int pa = sw_[q0 + UQ + l / (4 * NV)].atom;
-          const char* pl = reinterpret_cast<const char*>(P.Gp) + (size_t)pa * (KP * sizeof(T)) + (l % (4 * NV)) * 128;
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(pl));
-        }
         SlotW<T> e[UQ];
 #pragma unroll
         for (int t = 0; t < UQ; t += 2) {
           const float4 e2 = *reinterpret_cast<const float4*>(sw_ + q0 + t);
           e[t].atom = __float_as_int(e2.x); e[t].w = e2.y; e[t + 1].atom = __float_as_int(e2.z); e[t + 1].w = e2.w;
         }
-        float4 gv[UQ][NV];
+        RowV gv[UQ][NV];
 #pragma unroll
         for (int t = 0; t < UQ; ++t) {
-          const float4* row = reinterpret_cast<const float4*>(Grl + (unsigned long long)(unsigned)e[t].atom * (unsigned)(KP * sizeof(T)));
+          const RowV* row = reinterpret_cast<const RowV*>(Grl + (unsigned long long)(unsigned)e[t].atom * (unsigned)(KP * sizeof(T)));
 #pragma unroll
-          for (int v = 0; v < NV; ++v) gv[t][v] = (t < nr) ? ld_global_vec(row + v * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int v = 0; v < NV; ++v) {
+            if (t < nr) gv[t][v] = ld_global_vec(row + v * 32);
+            else row_zero(gv[t][v]);
+          }
         }
 #pragma unroll
         for (int t = 0; t < UQ; ++t) {
           const float2 ww = make_float2(e[t].w, e[t].w);
 #pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            corr2[2 * v] = ffma2(make_float2(gv[t][v].x, gv[t][v].y), ww, corr2[2 * v]);
-            corr2[2 * v + 1] = ffma2(make_float2(gv[t][v].z, gv[t][v].w), ww, corr2[2 * v + 1]);
-          }
+          for (int v = 0; v < NV; ++v) row_fma(&corr2[PV * v], gv[t][v], ww);
         }
       }
 
@@ -617,7 +643,7 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
       T* hrow = P.Ht + (size_t)col * k;
       if (k == KP) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) *reinterpret_cast<float4*>(hrow + (v * 32 + l) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int v = 0; v < NV; ++v) { RowV z; row_zero(z); *reinterpret_cast<RowV*>(hrow + (v * 32 + l) * LW) = z; }
       } else {
 #pragma unroll
         for (int m = 0; m < NA; ++m) {

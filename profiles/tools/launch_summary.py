@@ -28,7 +28,7 @@ for s in range(first, len(starts)):
         n = n[:n.index("(")] if "(" in n else n
         agg[n] = agg.get(n, 0.0) + ms
     tot = sum(agg.values())
-    lars = sum(v for k, v in agg.items() if "lars_kernel" in k)
+    lars = sum(v for k, v in agg.items() if "lars_" in k)
     print("\n## step %d (timed step %d): %.2f ms of kernel time, LARS coder share %.1f%%\n" % (s + 1, s - first + 1, tot, 100 * lars / tot))
     print("| kernel | ms | share |\n|---|---:|---:|")
     for k, v in sorted(agg.items(), key=lambda x: -x[1]):
