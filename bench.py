@@ -375,7 +375,7 @@ def run_ours(args):
     for hbuf in host:
         hbuf.copy_(pool)                                   # synthetic host-resident minibatches
     W_host = torch.empty(d, k, dtype=dt).pin_memory()
-    e2e_steps = max(3, min(K, 8))
+    e2e_steps = max(3, min(K, 20))
     e2e_warm = 6 if graph_mode else 2          # graph mode: every (staging buffer, parity) key is captured on its second sight
     for i in range(e2e_warm):
         t += 1
