@@ -360,8 +360,11 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
       }
     }
   };
-  // u_p = sum_{p <= i < lim} V[p][i] src[i]
-  auto sweep_u = [&](double (&u)[SA], const double* src, int nW, int lim, bool on) {
+  // u_p = sum_{p <= i < lim} V[p][i] src[i]; *ssq (when given) receives sum_i src[i]^2 in ascending order -- every lane
+  // reads the whole source vector anyway, so |t|^2 of a join costs no cross-lane reduction (entries beyond a group's own
+  // count are exact zeros)
+  auto sweep_u = [&](double (&u)[SA], const double* src, int nW, int lim, bool on, double* ssq = nullptr) {
+    double sq = 0.0;
     int pe[SA];
 #pragma unroll
     for (int m = 0; m < SA; ++m) pe[m] = on ? (l + LPC * m) : 0x7fffffff;
@@ -372,12 +375,14 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
 #pragma unroll 4
     for (int i = 0; i < nS1; ++i) {
       const double si = src[i];
+      sq = fma(si, si, sq);
       if (pe[0] <= i && (LPC == 32 || i < lim_e)) u[0] += rp[0] * si;
       rp += i + 1;
     }
 #pragma unroll 2
     for (int i = nS1; i < nS; ++i) {
       const double si = src[i];
+      sq = fma(si, si, sq);
 #pragma unroll
       for (int m = 0; m < SA; ++m)
         if (LPC * m <= i && pe[m] <= i && (LPC == 32 || i < lim_e)) u[m] += rp[LPC * m] * si;
@@ -388,12 +393,14 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
 #pragma unroll 2
       for (int i = SPLIT; i < nW; ++i) {
         const double si = src[i];
+        sq = fma(si, si, sq);
 #pragma unroll
         for (int m = 0; m < SA; ++m)
           if (LPC * m <= i && pe[m] <= i && (LPC == 32 || i < lim_e)) u[m] += rp[LPC * m] * si;
         rp += i + 1;
       }
     }
+    if (ssq) *ssq = sq;
   };
   auto Vld = [&](int idx) -> double { return (SPLIT > 0 && idx >= MSM) ? Mx[idx - MSM] : Mg[idx]; };
   auto Vst = [&](int idx, double v) {
@@ -416,15 +423,12 @@ __global__ void __launch_bounds__(LARS_MAX_THREADS, 1) lars_kernel(LarsParams<T>
 #pragma unroll
     for (int m = 0; m < SA; ++m) { t[m] = 0.0; u[m] = 0.0; }
     sweep_t(t, gs, sW, s, on);
-    double tt = 0.0;
 #pragma unroll
-    for (int m = 0; m < SA; ++m) {
-      tt += t[m] * t[m];
+    for (int m = 0; m < SA; ++m)
       if (LPC * m < sW) us[l + LPC * m] = t[m];
-    }
-    tt = gsum<LPC>(tt);
     __syncwarp();
-    sweep_u(u, us, sW, s, on);
+    double tt = 0.0;
+    sweep_u(u, us, sW, s, on, &tt);
     return (on ? Gd(a, a) : 1.0) - tt;
   };
 

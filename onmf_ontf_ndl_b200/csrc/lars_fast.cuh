@@ -167,7 +167,9 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
   };
   // u_p = sum_{p <= i < s} V[p][i] src[i].  Two columns per step: the columns i, i + 1 of an even i have the same padded
   // length i + 2 (row i + 1 of column i is the zero pad; src[s] = 0 when s is odd, the column behind it is finite).
-  auto sweep_u = [&](double (&u)[SA], const double* src, int s) {
+  // *ssq (when given) receives sum_i src[i]^2, ascending (the general kernel's order): |t|^2 of a join without a reduction
+  auto sweep_u = [&](double (&u)[SA], const double* src, int s, double* ssq = nullptr) {
+    double sq = 0.0;
     const double2* src2 = reinterpret_cast<const double2*>(src);
     const int nS = s > SPLIT ? SPLIT : s;
     const int nS1 = nS < 32 ? nS : 32;
@@ -176,6 +178,8 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
 #pragma unroll 2
     for (; i < nS1; i += 2) {
       const double2 sp = src2[i >> 1];
+      sq = fma(sp.x, sp.x, sq);
+      sq = fma(sp.y, sp.y, sq);
       if (l <= i + 1) {
         u[0] += rp[0] * sp.x;
         u[0] += rp[i + 2] * sp.y;
@@ -185,6 +189,8 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
 #pragma unroll 2
     for (; i < nS; i += 2) {
       const double2 sp = src2[i >> 1];
+      sq = fma(sp.x, sp.x, sq);
+      sq = fma(sp.y, sp.y, sq);
 #pragma unroll
       for (int m = 0; m < SA; ++m)
         if (l + 32 * m <= i + 1) {
@@ -198,12 +204,14 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
 #pragma unroll 2
       for (i = SPLIT; i < s; ++i) {
         const double si = src[i];
+        sq = fma(si, si, sq);
 #pragma unroll
         for (int m = 0; m < SA; ++m)
           if (l + 32 * m <= i) u[m] += rp[32 * m] * si;
         rp += (i + 2) & ~1;
       }
     }
+    if (ssq) *ssq = sq;
   };
 
   unsigned long long st_knots = 0, st_s = 0, st_s2 = 0, st_drops = 0, st_cols = 0, st_ovf = 0;
@@ -319,24 +327,16 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
         }
         __syncwarp();
         sweep_t(t, gs, s);
-        double tt = 0.0;
 #pragma unroll
-        for (int m = 0; m < SA; ++m) {
-          tt += t[m] * t[m];
+        for (int m = 0; m < SA; ++m)
           if (32 * m < s) us[l + 32 * m] = t[m];      // (zero beyond s: the paired sweep reads us[s] when s is odd)
-        }
         __syncwarp();
-        sweep_u(u, us, s);
+        double tt = 0.0;
+        sweep_u(u, us, s, &tt);                        // |t|^2 comes with the sweep: every lane reads all of t
         double su = 0.0;
 #pragma unroll
         for (int m = 0; m < SA; ++m) su += u[m];
-        // |t|^2 and 1^T u: one butterfly, two values in flight
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          const double a = __shfl_xor_sync(0xffffffffu, tt, off);
-          const double b = __shfl_xor_sync(0xffffffffu, su, off);
-          tt += a; su += b;
-        }
+        su = gsum<32>(su);                             // 1^T u (a shuffle is an L1-pipe wavefront: one reduction, not two)
         const double sig = gjj - tt;
         double asig = fabs(sig);
         asig = asig > 4.930380657631324e-32 ? asig : 4.930380657631324e-32;
