@@ -992,23 +992,47 @@ static size_t ovf_scratch_groups(int kp) {
 }
 
 // fast first tier: (threads per CTA, columns of V in shared memory, Gram rows in flight) variants
-template <int NA, int SMAX, int SPLIT, int NT, int UQ, int LW = 4, bool NOAL = false>
+template <int NA, int SMAX, int SPLIT, int NT, int UQ, int LW = 4, bool NOAL = false, bool GSM = false>
 static int launch_fast_variant(const LarsParams<float>& P, long long n_upper, cudaStream_t st) {
-  auto kern = lars_fast_kernel<NA, SMAX, SPLIT, NT, UQ, LW, NOAL>;
+  auto kern = lars_fast_kernel<NA, SMAX, SPLIT, NT, UQ, LW, NOAL, GSM>;
+  const size_t g_bytes = GSM ? round_up<size_t>((size_t)P.k * (32 * NA) * sizeof(float), 128) : 0;
   int nw = NT / 32;
+  if (GSM) {                                            // as many warps as fit beside the staged Gram
+    const long fit = ((long)max_smem_optin() - (long)g_bytes - 256) / (long)(fast_group_words<SMAX, SPLIT>() * 4);
+    if (fit < nw) nw = (int)fit;
+    if (nw < 1) return fail(ONMF_E_UNSUPPORTED, "lasso_lars: fast tier does not fit in shared memory");
+  }
   const long long per_sm = cdiv<long long>(n_upper, num_sms());          // spread small minibatches over all SMs
   if (per_sm < nw) nw = per_sm < 1 ? 1 : (int)per_sm;
   const long long grid_ll = cdiv<long long>(n_upper, nw);
   int sms = num_sms() - g_lars_reserved_sms;
   if (sms < 1) sms = 1;
   const int grid = grid_ll > sms ? sms : (int)grid_ll;
-  const size_t smem = (size_t)nw * fast_group_words<SMAX, SPLIT>() * 4;
+  const size_t smem = g_bytes + (size_t)nw * fast_group_words<SMAX, SPLIT>() * 4;
   if ((long)smem > max_smem_optin()) return fail(ONMF_E_UNSUPPORTED, "lasso_lars: fast tier does not fit in shared memory");
   ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, nw * 32, smem, st>>>(P);
   ONMF_LAUNCH_CHECK("lars_fast_kernel");
   return ONMF_OK;
 }
+// k <= 128 (4 atoms per lane, Gram staged in shared memory): 32 slots, the whole factor in shared memory; the kernel needs few
+// registers, and these minibatches are small enough to be latency-bound (a handful of columns per warp), so it runs
+// with as many warps as the register file allows
+template <int SMAX>
+static int launch_fast_gsm(const LarsParams<float>& P, long long n_upper, cudaStream_t st) {
+#ifdef LARS_FAST_EXPERIMENT
+  static int cfg = -1;
+  if (cfg < 0) { const char* e = getenv("ONMF_FAST_CFG"); cfg = e ? atoi(e) : 0; }
+  switch (cfg) {
+    case 1: return launch_fast_variant<4, SMAX, SMAX, 1024, 4, 4, true, true>(P, n_upper, st);
+    case 2: return launch_fast_variant<4, SMAX, SMAX, 640, 4, 4, true, true>(P, n_upper, st);
+    case 3: return launch_fast_variant<4, SMAX, SMAX, 512, 4, 4, true, true>(P, n_upper, st);
+    case 4: return launch_fast_variant<4, SMAX, SMAX, 1024, 2, 4, true, true>(P, n_upper, st);
+  }
+#endif
+  return launch_fast_variant<4, SMAX, SMAX, 768, 4, 4, true, true>(P, n_upper, st);     // (cfg4: 0.274 ms; 1024 / 640 / 512 threads: 0.286 / 0.277 / 0.290)
+}
+
 #ifdef LARS_FAST_EXPERIMENT
 constexpr int FAST_MAX_WARPS = 32, FAST_MIN_SPLIT = 16;
 #else
@@ -1075,6 +1099,10 @@ static int launch_tier(LarsParams<T> P, long long n_upper, int max_warps, cudaSt
   if constexpr (std::is_same<T, float>::value && LPC == 32 && SPLIT > 0 && !MGLOB) {
     // fp32 production path, k > 128: the warp-uniform fast tier walks the clean paths and hands everything else on
     if (!gsm && P.G64 != nullptr && P.ovf_list != nullptr && g_lars_fast && k > SMAX) return launch_fast<NA, SMAX>(P, n_upper, st);
+  }
+  if constexpr (std::is_same<T, float>::value && LPC == 32 && NA == 4 && SMAX == 32 && SPLIT == 0 && !MGLOB) {
+    // fp32, 64 < k <= 128: first tier (32 slots) by the fast kernel with the Gram in shared memory
+    if (gsm && P.G64 != nullptr && P.ovf_list != nullptr && g_lars_fast && P.col_list == nullptr) return launch_fast_gsm<SMAX>(P, n_upper, st);
   }
   if (gsm) {
     auto kern = lars_kernel<T, LPC, NA, SMAX, true, MGLOB, SPLIT>;

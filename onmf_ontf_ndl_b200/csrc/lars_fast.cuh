@@ -67,7 +67,7 @@ __host__ __device__ constexpr int fast_group_words() { return 2 * fast_cpad(SPLI
 template <int SMAX, int SPLIT>
 __host__ __device__ constexpr int fast_tail_doubles() { return fast_cpad(SMAX) - fast_cpad(SPLIT); }
 
-template <int NA, int SMAX, int SPLIT, int NT, int UQ, int LW = 4, bool NOAL = false>
+template <int NA, int SMAX, int SPLIT, int NT, int UQ, int LW = 4, bool NOAL = false, bool GSM = false>
 __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
   typedef float T;
   constexpr int SA = SMAX / 32;          // slot registers per lane (slot p = l + 32 m)
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
   constexpr int NV = NA / LW;            // loads per Gram row per lane
   constexpr int PV = LW / 2;             // atom pairs per load
   constexpr int KP = 32 * NA;            // padded row length of the Gram copy
-  static_assert(SMAX % 32 == 0 && NA % 4 == 0 && SPLIT % 2 == 0 && SPLIT < SMAX, "bad tile shape");
+  static_assert(SMAX % 32 == 0 && NA % 4 == 0 && SPLIT % 2 == 0 && SPLIT <= SMAX, "bad tile shape");
 
   if (P.hint != nullptr && *P.hint != (unsigned)P.run_if) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -83,7 +83,10 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
   int l = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   asm volatile("" : "+r"(l));            // (opaque: keeps the lane index in a register instead of re-reading %tid in the loops)
-  uint32_t* gbase = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * fast_group_words<SMAX, SPLIT>();
+  // GSM (k <= 128): the padded fp32 Gram is staged once per CTA in shared memory (as the general kernel does), rows are LDS.128
+  T* Gs = reinterpret_cast<T*>(smem_raw);
+  const size_t g_bytes = GSM ? round_up<size_t>((size_t)k * KP * sizeof(T), 128) : 0;
+  uint32_t* gbase = reinterpret_cast<uint32_t*>(smem_raw + g_bytes) + (size_t)warp * fast_group_words<SMAX, SPLIT>();
   constexpr int MSMP = fast_cpad(SPLIT);                                           // doubles of V kept in shared memory
   double* Mg = reinterpret_cast<double*>(gbase);                                   // columns 0..SPLIT-1 of V
   double* Mx = P.Mhyb + ((size_t)blockIdx.x * (blockDim.x / 32) + warp) * (size_t)fast_tail_doubles<SMAX, SPLIT>();   // columns >= SPLIT
@@ -96,6 +99,18 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
   auto atom_of = [&](int m) -> int { return ((m / LW) * 32 + l) * LW + (m % LW); };
   unsigned long long Grl = reinterpret_cast<unsigned long long>(P.Gp) + (unsigned long long)l * sizeof(RowV);
   asm volatile("" : "+l"(Grl));
+  if (GSM) {
+    for (int idx = threadIdx.x; idx < k * KP; idx += blockDim.x) {
+      const int a = idx / KP, i = idx - a * KP;
+      Gs[idx] = (i < k) ? (T)P.G64[(size_t)a * k + i] : T(0);
+    }
+    __syncthreads();
+  }
+  // piece v of this lane's part of Gram row a
+  auto row_piece = [&](int a, int v) -> RowV {
+    if (GSM) return *reinterpret_cast<const RowV*>(Gs + (size_t)a * KP + (v * 32 + l) * LW);
+    return ld_global_vec(reinterpret_cast<const RowV*>(Grl + (unsigned long long)(unsigned)a * (unsigned)(KP * sizeof(T))) + v * 32);
+  };
   const double* __restrict__ G64 = P.G64;
 
   const T tiny = T(1.1754943508222875e-38);
@@ -367,10 +382,10 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
       RowV gv0[UQ][NV];
 #pragma unroll
       for (int t = 0; t < UQ; ++t) {
-        const RowV* row = reinterpret_cast<const RowV*>(Grl + (unsigned long long)(unsigned)sw_[t].atom * (unsigned)(KP * sizeof(T)));
+        const int a0 = sw_[t].atom;
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-          if (t < n_act) gv0[t][v] = ld_global_vec(row + v * 32);
+          if (t < n_act) gv0[t][v] = row_piece(a0, v);
           else row_zero(gv0[t][v]);
         }
       }
@@ -420,10 +435,9 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
         RowV gv[UQ][NV];
 #pragma unroll
         for (int t = 0; t < UQ; ++t) {
-          const RowV* row = reinterpret_cast<const RowV*>(Grl + (unsigned long long)(unsigned)e[t].atom * (unsigned)(KP * sizeof(T)));
 #pragma unroll
           for (int v = 0; v < NV; ++v) {
-            if (t < nr) gv[t][v] = ld_global_vec(row + v * 32);
+            if (t < nr) gv[t][v] = row_piece(e[t].atom, v);
             else row_zero(gv[t][v]);
           }
         }
@@ -621,7 +635,7 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
         __syncwarp();
         // exact covariance of the dropped atom (sklearn _least_angle.py:891)
         T part = T(0);
-        const T* grow = P.Gp + (size_t)a_d * KP;
+        const T* grow = (GSM ? Gs : P.Gp) + (size_t)a_d * KP;
 #pragma unroll
         for (int m = 0; m < SA; ++m) {
           if (32 * m < n_act) {

@@ -891,7 +891,7 @@ def test_minibatch_by_reference_engine_matches_presplit_engine(monkeypatch, gold
 
 
 def test_fast_tier_matches_general_kernel():
-    """csrc/lars_fast.cuh (the warp-uniform first tier of the fp32 coder for k > 128) against the general kernel on the same
+    """csrc/lars_fast.cuh (the warp-uniform first tier of the fp32 coder for k > 64) against the general kernel on the same
     covariances: learned unit-norm dictionaries (clean paths, <= 64 active atoms), a raw U[0,1) dictionary (most columns
     outgrow the 64 slots and are handed on), alpha = 0 (long paths, degenerate tails), k < 256 (padded lanes) and the
     k <= 512 class."""
@@ -911,7 +911,10 @@ def test_fast_tier_matches_general_kernel():
         return Ht, stats.cpu().numpy()
     assert _lib.get_option(_lib.OPT_LARS_FAST_TIER) == 1                 # the default
     for (d, k, n, alpha, unit) in [(1024, 256, 3000, 1.0, True), (1024, 256, 300, 1.0, False), (256, 200, 500, 0.0, True),
-                                   (512, 160, 700, 0.3, True), (300, 384, 400, 0.5, True)]:
+                                   (512, 160, 700, 0.3, True), (300, 384, 400, 0.5, True),
+                                   # 64 < k <= 128: the shared-memory-Gram form of the fast tier (32 slots)
+                                   (400, 100, 3000, 1.0, True), (200, 128, 500, 0.2, True), (300, 70, 300, 0.0, True),
+                                   (400, 100, 200, 1.0, False)]:
         W = rng.random((d, k))
         if unit:
             W /= np.linalg.norm(W, axis=0)
