@@ -13,8 +13,8 @@ p8 = torch.randint(0, 256, (n, d), dtype=torch.uint8, device=dev, generator=g)
 host8 = [p8.cpu().pin_memory(), torch.randint(0, 256, (n, d), dtype=torch.uint8).pin_memory()]
 dev8 = [h.to(dev) for h in host8]
 W_host = torch.empty(d, k).pin_memory()
-for mode in ('resident', 'host', 'host_noW', 'resident'):
-    eng = OnmfEngine(d, k, alpha=1.0, dtype=torch.float32, device=dev, lars_timing=True)
+for mode, kw in (('resident', {}), ('host', {}), ('host', dict(graph=False)), ('host', dict(graph=False, collect_stats=True)), ('host_noW', dict(graph=False, collect_stats=True)), ('resident', dict(graph=False, collect_stats=True))):
+    eng = OnmfEngine(d, k, alpha=1.0, dtype=torch.float32, device=dev, lars_timing=True, **kw)
     eng.set_state(W)
     t = 0
     def one(i):
@@ -36,4 +36,4 @@ for mode in ('resident', 'host', 'host_noW', 'resident'):
         one(i)
     eng.flush(); e1.record(eng.main); torch.cuda.synchronize()
     lm = eng._plan.lars_ms()
-    print('%-9s %.3f ms/step; coder ms: mean %.3f min %.3f max %.3f (%d)' % (mode, e0.elapsed_time(e1) / 20, sum(lm) / max(len(lm), 1), min(lm), max(lm), len(lm)))
+    print('%-9s %-45s %.3f ms/step; coder ms: mean %.3f min %.3f max %.3f (%d)' % (mode, str(kw), e0.elapsed_time(e1) / 20, sum(lm) / max(len(lm), 1), min(lm), max(lm), len(lm)))
