@@ -928,3 +928,43 @@ def test_fast_tier_matches_general_kernel():
         assert not torch.isnan(H1).any() and not torch.isnan(H0).any()   # every column written by some tier
         assert s1[0] == n and s0[0] == n, (s1, s0)                       # columns finished
         assert torch.equal(H1, H0), (d, k, n, alpha, float((H1 - H0).abs().max()), int((H1 != H0).any(1).sum()))
+
+
+def test_fast_tier_edge_columns():
+    """Columns that leave the clean path or stop at once, through the fast tier and through the general kernel: an all-zero
+    and an all-negative covariance row (empty code), alpha above every covariance, exact ties from a duplicated atom
+    (degenerate pivot: handed to the general tier), max_iter = 1 and 3 (every column handed on), a tiny alpha.  Same bits,
+    every column finished, no hang."""
+    rng = np.random.default_rng(33)
+    for (d, k) in ((256, 200), (160, 100)):
+        n = 64
+        W = rng.random((d, k)); W /= np.linalg.norm(W, axis=0)
+        W[:, 7] = W[:, 3]                                             # two identical atoms
+        X = rng.random((n, d))
+        X[0] = 0.0
+        Wt = tt(W, torch.float32)
+        G64 = (Wt.double().T @ Wt.double()).contiguous()
+        G64 = ((G64 + G64.T) / 2).contiguous()
+        Ct = (tt(X, torch.float32) @ Wt).contiguous()
+        Ct[1] = -Ct[1]                                                # nothing is positively correlated
+        Ct[2] = 0.0
+        for alpha, max_iter in ((1.0, 1000), (1e4, 1000), (1e-3, 1000), (0.5, 1), (0.5, 3)):
+            outs = []
+            for fast in (1, 0):
+                Ht = torch.full((n, k), float("nan"), device=dev())
+                ws = torch.zeros(_lib.lasso_lars_workspace(torch.float32, k, n), dtype=torch.uint8, device=dev())
+                stats = torch.zeros(8, dtype=torch.int64, device=dev())
+                saved = _lib.get_option(_lib.OPT_LARS_FAST_TIER)
+                _lib.set_option(_lib.OPT_LARS_FAST_TIER, fast)
+                try:
+                    _lib.lasso_lars(G64, Ct, d, alpha, Ht, ws, max_iter=max_iter, stats=stats)
+                    torch.cuda.synchronize()
+                finally:
+                    _lib.set_option(_lib.OPT_LARS_FAST_TIER, saved)
+                assert not torch.isnan(Ht).any() and int(stats[0]) == n
+                outs.append(Ht)
+            assert torch.equal(outs[0], outs[1]), (d, k, alpha, max_iter)
+            assert float(outs[0][0].abs().max()) == 0.0 and float(outs[0][1].abs().max()) == 0.0 and float(outs[0][2].abs().max()) == 0.0
+            if alpha == 1e4:
+                assert float(outs[0].abs().max()) == 0.0
+            assert float(outs[0].min()) >= 0.0
