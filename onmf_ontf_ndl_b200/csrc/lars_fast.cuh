@@ -1,22 +1,28 @@
 // K3, fast first tier -- included by lars.cu (inside namespace onmf).
 //
-// The fp32 production coder for k > 128 (one warp per column, 64 slots, hybrid shared/global factor) rewritten around
-// WARP-UNIFORM control flow: with one column per warp every path decision (join / drop / stop) is the same for all 32
-// lanes, so the knot loop is plain branches instead of the predicated, vote-guarded form the general kernel
-// (lars_kernel: several columns per warp, both precisions, every k class) needs.  It walks the CLEAN homotopy path only:
-// a column that meets any of sklearn's special events -- degenerate pivot (_least_angle.py:723-742), "alpha increasing"
-// bail-out (:752-765), max_iter, a numerically singular active block -- or outgrows the 64 slots is handed, untouched, to
-// the next tier (the general kernel, which re-walks it from the start with the full semantics); a few columns in 10^5.
-// The arithmetic of a clean path is the general kernel's, operation for operation (same reduction trees, same
-// accumulation order), so both produce the same bits; tests/test_gpu_parity.py::test_fast_tier_matches_general_kernel.
+// The fp32 production coder for k > 64 (one warp per column) rewritten around WARP-UNIFORM control flow: with one column
+// per warp every path decision (join / drop / stop) is the same for all 32 lanes, so the knot loop is plain branches
+// instead of the predicated, vote-guarded form the general kernel (lars_kernel: several columns per warp, both precisions,
+// every k class) needs.  It walks the CLEAN homotopy path only: a column that meets any of sklearn's special events --
+// degenerate pivot (_least_angle.py:723-742), "alpha increasing" bail-out (:752-765), max_iter, a numerically singular active
+// block -- or outgrows the slots of this tier is handed, untouched, to the next tier (the general kernel, which re-walks it
+// from the start with the full semantics); a few columns in 10^5.  The arithmetic of a clean path is the general kernel's,
+// operation for operation (same reduction trees, same accumulation order), so both produce the same bits;
+// tests/test_gpu_parity.py::test_fast_tier_matches_general_kernel, ::test_fast_tier_edge_columns.
 //
-// Per knot (s = active atoms, NA = k/32 atoms per lane):
-//   arg-max of the inactive covariances   NA FMNMX + 2 REDUX
-//   join: g = G64[j, A] (one gather), t = V^T g, u = V t over the packed FP64 inverse factor (shared memory, columns
-//         >= SPLIT in an L2-resident tail), |t|^2 and 1^T u reduced TOGETHER (one butterfly with two values in flight)
-//   equiangular weights (incremental), normalisation, slot table
-//   correlation pass G[:, A] w: float4 Gram-row loads UQ rows deep, packed FFMA2 (two fp32 FMAs per instruction)
-//   step length: packed add / mul, MUFU.RCP, REDUX min
+// Two instantiations (lars.cu::launch_fast / launch_fast_gsm):
+//   k > 128 (NA = 8 / 16 atoms per lane): 64 slots, the first SPLIT columns of the factor in shared memory and the rest in an
+//       L2-resident tail, Gram rows through L1 (zero-padded global copy);
+//   64 < k <= 128 (NA = 4, GSM): 32 slots, the whole factor and the Gram in shared memory.
+//
+// What it is bound by (profiles/r2_lars_fast.md): the L1 data pipe -- LDG, LDS, STS and SHFL all cost wavefronts there, and
+// 45 % of them are the Gram rows of the correlation pass (4 bytes per multiply-add, the algorithmic minimum).  Hence:
+//   arg-max of the inactive covariances   FMNMX3 + 2 REDUX (no memory traffic)
+//   join: g = G64[j, A] (one gather), t = V^T g, u = V t over the packed FP64 inverse factor read in 16-byte pairs; |t|^2 is
+//         accumulated inside the second sweep (every lane reads all of t), 1^T u is the one shuffle reduction of a knot
+//   equiangular weights (incremental), normalisation, slot table (two entries per LDS.128)
+//   correlation pass G[:, A] w: rows of occupied slots only, 16-byte loads UQ rows deep, packed FFMA2
+//   step length: packed FADD2 / FMUL2, MUFU.RCP, one unsigned minimum per pair, REDUX min
 //   a drop (one per ~30 knots) runs the general kernel's Givens downdate
 
 // a warp-uniform decision, stated so that the compiler can see it (a vote result is uniform by construction): keeps the
