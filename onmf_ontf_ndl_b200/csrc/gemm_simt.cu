@@ -15,15 +15,15 @@
 
 namespace onmf {
 
-constexpr int BM = 128, BK = 16, NT = 256, TM = 8;
+constexpr int BM = 128, BK = 16, NT = 256;      // BM: the large row tile (64 and 32 for few rows / few CTAs, see launch_gemm)
 
 // C[M x N] (+ split z) = op(A) . B ; A is (M x K) row-major (AKM=false) or (K x M) row-major (AKM=true);
 // B is (K x N) row-major with leading dim ldb; C row-major with leading dim ldc.
-template <typename T, int BN, bool AKM>
+template <typename T, int BN, bool AKM, int BM = 128>
 __global__ void __launch_bounds__(NT) gemm_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb,
                                                   T* __restrict__ C, int ldc, long long M, int N, long long K,
                                                   long long kchunk, long long split_stride) {
-  constexpr int TN = BN / 16;
+  constexpr int TN = BN / 16, TM = BM / 16;
   __shared__ T As[BK][BM + 4];
   __shared__ T Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -42,19 +42,20 @@ __global__ void __launch_bounds__(NT) gemm_kernel(const T* __restrict__ A, int l
   for (long long k0 = kbeg; k0 < kend; k0 += BK) {
     if (AKM) {
       // A tile BK x BM from rows k0.., contiguous along M
-      const int kk = tid >> 4, mm = (tid & 15) * 8;
+      const int kk = tid >> 4, mm = (tid & 15) * TM;
       const long long kr = k0 + kk;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < TM; ++e) {
         long long m = m0 + mm + e;
         As[kk][mm + e] = (kr < kend && m < M) ? A[kr * lda + m] : T(0);
       }
     } else {
-      // A tile BM x BK from row-major (M x K): thread -> (row, 8 consecutive k)
-      const int row = tid >> 1, kq = (tid & 1) * 8;
+      // A tile BM x BK from row-major (M x K): thread -> (row, EK consecutive k)
+      constexpr int TPR = NT / BM, EK = BK / TPR;
+      const int row = tid / TPR, kq = (tid % TPR) * EK;
       const long long m = m0 + row;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
+      for (int e = 0; e < EK; ++e) {
         long long kr = k0 + kq + e;
         As[kq + e][row] = (m < M && kr < kend) ? A[m * lda + kr] : T(0);
       }
@@ -157,25 +158,30 @@ static int launch_gemm(const T* A, int lda, const T* B, int ldb, T* C, int ldc, 
   long long kchunk = round_up<long long>(cdiv<long long>(K, splits), BK);
   if (kchunk < BK) kchunk = BK;
   dim3 block(NT);
-  if (N <= 32) {
-    dim3 grid((unsigned)cdiv<long long>(M, BM), (unsigned)cdiv(N, 32), splits);
-    gemm_kernel<T, 32, AKM><<<grid, block, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kchunk, split_stride);
-  } else if (N <= 64) {
-    dim3 grid((unsigned)cdiv<long long>(M, BM), (unsigned)cdiv(N, 64), splits);
-    gemm_kernel<T, 64, AKM><<<grid, block, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kchunk, split_stride);
-  } else {
-    dim3 grid((unsigned)cdiv<long long>(M, BM), (unsigned)cdiv(N, 128), splits);
-    gemm_kernel<T, 128, AKM><<<grid, block, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kchunk, split_stride);
-  }
+  const int bn = N <= 32 ? 32 : N <= 64 ? 64 : 128;
+  // row tile: 32 / 64 rows when the product has no more (the surrogate sums of the small dictionaries: M = k <= 64 -- a
+  // 128-row tile would compute 2-5 x the needed entries), 64 rows when 128-row tiles would leave SMs without a CTA.  The
+  // order of the k-loop inside a CTA does not depend on the tile, so the results do not either.
+  const long long ctas128 = cdiv<long long>(M, 128) * cdiv(N, bn) * splits;
+  const int bm = M <= 32 ? 32 : (M <= 64 || ctas128 < num_sms()) ? 64 : 128;
+  dim3 grid((unsigned)cdiv<long long>(M, bm), (unsigned)cdiv(N, bn), splits);
+#define ONMF_GEMM_CASE(BN_, BM_)                                                                                       \
+  if (bn == BN_ && bm == BM_) gemm_kernel<T, BN_, AKM, BM_><<<grid, block, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, kchunk, split_stride);
+  ONMF_GEMM_CASE(32, 32) ONMF_GEMM_CASE(32, 64) ONMF_GEMM_CASE(32, 128)
+  ONMF_GEMM_CASE(64, 32) ONMF_GEMM_CASE(64, 64) ONMF_GEMM_CASE(64, 128)
+  ONMF_GEMM_CASE(128, 32) ONMF_GEMM_CASE(128, 64) ONMF_GEMM_CASE(128, 128)
+#undef ONMF_GEMM_CASE
   ONMF_LAUNCH_CHECK("gemm_kernel");
   return ONMF_OK;
 }
 
 static int pick_splits(long long n, int k, int d) {
-  // enough CTAs to fill the GPU: tiles(M=k, N=k+d) * splits >= 2 * SMs, each split >= 256 samples
+  // enough CTAs to fill the GPU: tiles(M=k, N=k+d) * splits >= 2 * SMs, each split >= 64 samples (the small configurations
+  // -- 1,000 to 16,384 samples, k <= 100 -- have one or two output tiles: with 256 samples per split they ran on 4-8 CTAs and
+  // the two products took longer than the coder)
   long long tiles = cdiv(k, BM) * (cdiv(k, 128) + cdiv(d, 128));
   long long want = cdiv<long long>(2LL * num_sms(), tiles);
-  long long cap = cdiv<long long>(n, 256);
+  long long cap = cdiv<long long>(n, 64);
   long long s = want < cap ? want : cap;
   if (s < 1) s = 1;
   if (s > 256) s = 256;
