@@ -1033,6 +1033,15 @@ static int launch_fast_gsm(const LarsParams<float>& P, long long n_upper, cudaSt
   return launch_fast_variant<4, SMAX, SMAX, 768, 4, 4, true, true>(P, n_upper, st);     // (cfg4: 0.274 ms; 1024 / 640 / 512 threads: 0.286 / 0.277 / 0.290)
 }
 
+// k <= 64 on SMALL minibatches (at most one column per resident warp): these calls are latency-bound -- a handful of columns
+// per SM, each a serial path of ~15-30 knots -- and one column per warp in the fast kernel (2 atoms per lane, Gram in shared
+// memory) has the shorter knot than the general kernel's four / two columns per warp.  Larger minibatches stay with the
+// general kernel, whose packing wins on throughput.
+constexpr int FAST_SMALL_WARPS = 24;
+static int launch_fast_small(const LarsParams<float>& P, long long n_upper, cudaStream_t st) {
+  return launch_fast_variant<2, 32, 32, FAST_SMALL_WARPS * 32, 4, 2, true, true>(P, n_upper, st);
+}
+
 #ifdef LARS_FAST_EXPERIMENT
 constexpr int FAST_MAX_WARPS = 32, FAST_MIN_SPLIT = 16;
 #else
@@ -1171,6 +1180,15 @@ static int launch_class(const T* G, const double* G64, const T* Ct, long long n,
     return Q;
   };
   int rc = ONMF_OK;
+  if constexpr (std::is_same<T, float>::value && KP <= 64 && S0 == 32 && !GL) {
+    if (G64 != nullptr && g_lars_fast && first_tier <= 0 && n <= (long long)num_sms() * FAST_SMALL_WARPS && k <= 64) {
+      // fast tier over all columns, then the general kernel (the larger of its tiers) over the columns it handed on
+      rc = launch_fast_small(tier_params(0, 0, false, true, false), n, st);
+      if (rc) return rc;
+      constexpr int NEXT = S1 > 0 ? S1 : S0;
+      return launch_tier<T, LPC, NA, NEXT, false>(tier_params(1, 1, true, false, false), n, 32, st, &padded);
+    }
+  }
   if (adaptive || first == 0) {
     LarsParams<T> Q = tier_params(0, 0, false, S1 > 0, GL && S1 == 0);
     if (adaptive) { Q.hint = &hdr->hint; Q.run_if = 0; }

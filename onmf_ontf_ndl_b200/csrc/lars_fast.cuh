@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(NT, 1) lars_fast_kernel(LarsParams<float> P) {
   constexpr int NV = NA / LW;            // loads per Gram row per lane
   constexpr int PV = LW / 2;             // atom pairs per load
   constexpr int KP = 32 * NA;            // padded row length of the Gram copy
-  static_assert(SMAX % 32 == 0 && NA % 4 == 0 && SPLIT % 2 == 0 && SPLIT <= SMAX, "bad tile shape");
+  static_assert(SMAX % 32 == 0 && NA % LW == 0 && NA % 2 == 0 && SPLIT % 2 == 0 && SPLIT <= SMAX, "bad tile shape");
 
   if (P.hint != nullptr && *P.hint != (unsigned)P.run_if) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];

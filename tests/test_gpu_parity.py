@@ -968,3 +968,41 @@ def test_fast_tier_edge_columns():
             if alpha == 1e4:
                 assert float(outs[0].abs().max()) == 0.0
             assert float(outs[0].min()) >= 0.0
+
+
+def test_fast_tier_small_dictionaries():
+    """k <= 64 on small minibatches: one column per warp in the fast kernel (2 atoms per lane) against the general kernel
+    (4 / 2 columns per warp).  The slots sit on different lanes, so the FP64 sums of a join are taken in a different order:
+    agreement to rounding, not bit for bit; plus the C oracle on the same covariances."""
+    rng = np.random.default_rng(44)
+    for (d, k, n, alpha) in [(100, 25, 1000, 1.0), (300, 49, 3000, 1.0), (441, 25, 500, 0.5), (64, 20, 300, 0.0), (50, 33, 100, 0.3),
+                             (120, 64, 700, 1.0), (40, 32, 200, 0.0), (30, 7, 64, 0.1)]:
+        W = rng.random((d, k)); W /= np.linalg.norm(W, axis=0)
+        X = rng.random((n, d))
+        if n > 2:
+            X[1] = 0.0
+        Wt = tt(W, torch.float32)
+        G64 = (Wt.double().T @ Wt.double()).contiguous()
+        G64 = ((G64 + G64.T) / 2).contiguous()
+        Ct = (tt(X, torch.float32) @ Wt).contiguous()
+        outs = []
+        for fast in (1, 0):
+            Ht = torch.full((n, k), float("nan"), device=dev())
+            ws = torch.zeros(_lib.lasso_lars_workspace(torch.float32, k, n), dtype=torch.uint8, device=dev())
+            stats = torch.zeros(8, dtype=torch.int64, device=dev())
+            saved = _lib.get_option(_lib.OPT_LARS_FAST_TIER)
+            _lib.set_option(_lib.OPT_LARS_FAST_TIER, fast)
+            try:
+                _lib.lasso_lars(G64, Ct, d, alpha, Ht, ws, stats=stats)
+                torch.cuda.synchronize()
+            finally:
+                _lib.set_option(_lib.OPT_LARS_FAST_TIER, saved)
+            assert not torch.isnan(Ht).any() and int(stats[0]) == n, (d, k, n, alpha, fast, stats.cpu().numpy())
+            outs.append(Ht.cpu().numpy().astype(np.float64))
+        assert rel(outs[0], outs[1]) < 2e-5, (d, k, n, alpha, rel(outs[0], outs[1]))
+        assert (outs[0] >= 0).all()
+        # the oracle on the SAME fp32 covariances and the FP64 Gram
+        cs = Ct.cpu().numpy().astype(np.float64)
+        Gn = G64.cpu().numpy()
+        Href = np.stack([c_oracle_lars_single(Gn, cs[i], alpha, d) for i in range(min(n, 60))])
+        assert rel(outs[0][:Href.shape[0]], Href) < 2e-3, (d, k, n, alpha)
