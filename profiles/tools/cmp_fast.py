@@ -8,6 +8,7 @@ import torch
 from onmf_ontf_ndl_b200 import _lib, OnmfEngine
 d, k, n = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
+alpha = float(os.environ.get('CMP_ALPHA', '1.0'))      # (the engine trains with alpha 1; the compared coder calls use this one)
 dev = torch.device('cuda:0'); dt = torch.float32
 g = torch.Generator(device=dev); g.manual_seed(0)
 Xt = torch.rand(n, d, dtype=dt, device=dev, generator=g); W = torch.rand(d, k, dtype=dt, device=dev, generator=g)
@@ -24,7 +25,7 @@ for fast in (0, 1):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         eng.stats.zero_()
         eng.Ht.fill_(float('nan'))
-        e0.record(); _lib.lasso_lars(eng.G, eng.Ct[:n], d, 1.0, eng.Ht[:n], eng._ws_lars, stats=eng.stats); e1.record()
+        e0.record(); _lib.lasso_lars(eng.G, eng.Ct[:n], d, alpha, eng.Ht[:n], eng._ws_lars, stats=eng.stats); e1.record()
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     H = eng.Ht[:n].clone()
