@@ -111,6 +111,14 @@ size_t onmf_gram_f64_workspace(int d, int k);
 int onmf_gram_f64(int dtype_in, const void* W, int d, int k, double* G64, float* G32, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Spectral norm (largest singular value) of a sample-major n x k matrix M, written to the device double *out:
+ * sqrt(lambda_max(M^T M)) -- FP64 Gram, then lambda_max by repeated squaring + Rayleigh quotient in one CTA (relative
+ * error < 1e-5 for every spectrum).  replaces: np.linalg.norm(H1 - H1_old, 2) / np.linalg.norm(H1_old, 2), the stopping
+ * test of update_code_within_radius (src/onmf.py:265). */
+size_t onmf_spectral_norm_workspace(int64_t n, int k);
+int onmf_spectral_norm(int dtype, const void* M, int64_t n, int k, double* out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K3  batched positive LARS-lasso (the sparse coder)
  * replaces: SparseCoder(..., 'lasso_lars', positive_code=True).transform (src/ontf.py:79-86), i.e.

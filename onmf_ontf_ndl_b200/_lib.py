@@ -51,6 +51,8 @@ SIGNATURES = {
     "onmf_gram_f64": (_i, [_i, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "onmf_lasso_lars_g64": (_i, [_i, _vp, _vp, _i64, _i, _i, _dbl, _i, _vp, _vp, _sz, _vp, _i, _vp]),
     "onmf_cov": (_i, [_i, _vp, _i64, _i, _vp, _i, _vp, _vp]),
+    "onmf_spectral_norm_workspace": (_sz, [_i64, _i]),
+    "onmf_spectral_norm": (_i, [_i, _vp, _i64, _i, _vp, _vp, _sz, _vp]),
     "onmf_lasso_lars_workspace": (_sz, [_i, _i, _i64]),
     "onmf_lasso_lars": (_i, [_i, _vp, _vp, _i64, _i, _i, _dbl, _i, _vp, _vp, _sz, _vp, _vp]),
     "onmf_lasso_lars_ex": (_i, [_i, _vp, _vp, _i64, _i, _i, _dbl, _i, _vp, _vp, _sz, _vp, _i, _vp]),
@@ -284,6 +286,19 @@ def gram_f64(W, G64, workspace, G32=None, stream=None):
     _check(load().onmf_gram_f64(dt(W), _ptr(W), d, k, _ptr(G64), _ptr(G32), _ptr(workspace), workspace.numel(),
                                 _stream(stream)), "onmf_gram_f64")
     return G64
+
+
+def spectral_norm_workspace(n, k):
+    return int(load().onmf_spectral_norm_workspace(int(n), int(k)))
+
+
+def spectral_norm(M, out, workspace, stream=None):
+    """out (one device float64) = largest singular value of the sample-major matrix M (n x k)"""
+    _req(M, "M"); _req(out, "out", torch.float64); _req(workspace, "workspace", torch.uint8)
+    n, k = M.shape
+    _check(load().onmf_spectral_norm(dt(M), _ptr(M), n, k, _ptr(out), _ptr(workspace), workspace.numel(), _stream(stream)),
+           "onmf_spectral_norm")
+    return out
 
 
 def cov(Xt, W, Ct, stream=None):

@@ -243,14 +243,10 @@ class Online_NMF():
 ####################################
 # custom sparsecoder
 
-def _spectral_norm(M):
-    return torch.linalg.matrix_norm(M, ord=2)
-
-
 def _pgd_device(Xt, Wd, Ht, alpha, sub_iter, stopping_diff, r=None):
     """Outer loop of the reference's projected-gradient coder (src/onmf.py:252-268) around the onmf_pgd_sweep
     kernel.  The stopping test needs two spectral norms per outer iteration (np.linalg.norm(., 2),
-    src/onmf.py:265); they are taken with torch.linalg on the device.
+    src/onmf.py:265): onmf_spectral_norm (FP64 Gram + largest eigenvalue by repeated squaring, csrc/gemm_simt.cu).
 
     Radius mode (r is not None, src/onmf.py:260-263): the reference projects H1 back to within spectral distance r of
     H0 after every row update and then executes `H0 = H1`, which ALIASES the two arrays -- from the second row on the
@@ -263,18 +259,28 @@ def _pgd_device(Xt, Wd, Ht, alpha, sub_iter, stopping_diff, r=None):
     _lib.gram(Wd, G)
     _lib.cov(Xt, Wd, Ct)
     i, dist = 0, 1.0
+    n = Ht.shape[0]
+    ws_n = torch.empty(_lib.spectral_norm_workspace(max(n, 1), k), dtype=torch.uint8, device=Wd.device)
+    norms = torch.zeros(2, dtype=torch.float64, device=Wd.device)
+    H_old = torch.empty_like(Ht)
     while i < sub_iter and dist > stopping_diff:
-        H_old = Ht.clone()
+        H_old.copy_(Ht)
         if r is not None and i == 0:
             h_before = Ht[:, 0].clone()                          # row 0 of H = column 0 of the sample-major Ht
             _lib.pgd_sweep_rows(G, Ct, alpha, i, Ht, 0, 1)
             delta = Ht[:, 0] - h_before
-            dd = float(torch.linalg.vector_norm(delta))
+            _lib.spectral_norm(delta.contiguous().view(-1, 1), norms[:1], ws_n)      # 2-norm of the one changed row
+            dd = float(norms[0])
             Ht[:, 0] = h_before + (r / max(r, dd)) * delta
             _lib.pgd_sweep_rows(G, Ct, alpha, i, Ht, 1, k)
         else:
             _lib.pgd_sweep(G, Ct, alpha, i, Ht)
-        dist = float(_spectral_norm(Ht - H_old) / _spectral_norm(H_old))
+        if n > 0:
+            _lib.spectral_norm(H_old, norms[1:], ws_n)
+            _lib.axpby(1.0, Ht, -1.0, H_old)                     # H_old <- H1 - H1_old
+            _lib.spectral_norm(H_old, norms[:1], ws_n)
+            nn = norms.tolist()
+            dist = nn[0] / nn[1] if nn[1] > 0 else float("inf") if nn[0] > 0 else float("nan")
         i += 1
     return Ht
 

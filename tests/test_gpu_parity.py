@@ -1006,3 +1006,30 @@ def test_fast_tier_small_dictionaries():
         Gn = G64.cpu().numpy()
         Href = np.stack([c_oracle_lars_single(Gn, cs[i], alpha, d) for i in range(min(n, 60))])
         assert rel(outs[0][:Href.shape[0]], Href) < 2e-3, (d, k, n, alpha)
+
+
+def test_spectral_norm_kernel():
+    """onmf_spectral_norm (FP64 Gram + largest eigenvalue by repeated squaring) against numpy's SVD: generic, rank-one,
+    repeated and nearly repeated top singular values, a zero matrix, one column; fp32 and fp64 inputs."""
+    rng = np.random.default_rng(55)
+    cases = []
+    cases.append(rng.random((700, 25)))
+    cases.append(rng.standard_normal((64, 100)))
+    cases.append(np.outer(rng.random(300), rng.random(49)))                       # rank one
+    Q, _ = np.linalg.qr(rng.standard_normal((200, 30)))
+    cases.append(Q @ np.diag([3.0, 3.0, 3.0] + [1.0] * 27))                       # triple top singular value
+    cases.append(Q @ np.diag([2.0, 2.0 * (1 - 1e-4), 2.0 * (1 - 1e-5)] + list(np.linspace(1.9, 0.1, 27))))   # near-degenerate
+    cases.append(np.zeros((50, 7)))
+    cases.append(rng.random((1000, 1)))
+    cases.append(rng.random((3, 238)) * 1e-3)
+    for M in cases:
+        n, k = M.shape
+        ref = np.linalg.norm(M, 2)
+        for dt_ in (torch.float64, torch.float32):
+            Md = tt(M, dt_)
+            out = torch.full((1,), float("nan"), dtype=torch.float64, device=dev())
+            ws = torch.empty(_lib.spectral_norm_workspace(n, k), dtype=torch.uint8, device=dev())
+            _lib.spectral_norm(Md, out, ws)
+            got = float(out[0])
+            tol = 2e-5 if dt_ == torch.float64 else 1e-4
+            assert abs(got - ref) <= tol * max(ref, 1e-300) + (0 if ref > 0 else 1e-300), (n, k, dt_, got, ref)
