@@ -1036,7 +1036,8 @@ static int launch_fast_gsm(const LarsParams<float>& P, long long n_upper, cudaSt
 // k <= 64 on SMALL minibatches (at most one column per resident warp): these calls are latency-bound -- a handful of columns
 // per SM, each a serial path of ~15-30 knots -- and one column per warp in the fast kernel (2 atoms per lane, Gram in shared
 // memory) has the shorter knot than the general kernel's four / two columns per warp.  Larger minibatches stay with the
-// general kernel, whose packing wins on throughput.
+// general kernel, whose packing wins on throughput (measured: cfg2, k = 49, 27 columns per SM: 0.084 -> 0.065 ms; cfg3, k = 25,
+// 68 columns per SM: 0.087 -> 0.104 ms -- hence one column per warp slot for k <= 32, two for k <= 64).
 constexpr int FAST_SMALL_WARPS = 24;
 static int launch_fast_small(const LarsParams<float>& P, long long n_upper, cudaStream_t st) {
   return launch_fast_variant<2, 32, 32, FAST_SMALL_WARPS * 32, 4, 2, true, true>(P, n_upper, st);
@@ -1181,7 +1182,7 @@ static int launch_class(const T* G, const double* G64, const T* Ct, long long n,
   };
   int rc = ONMF_OK;
   if constexpr (std::is_same<T, float>::value && KP <= 64 && S0 == 32 && !GL) {
-    if (G64 != nullptr && g_lars_fast && first_tier <= 0 && n <= (long long)num_sms() * FAST_SMALL_WARPS && k <= 64) {
+    if (G64 != nullptr && g_lars_fast && first_tier <= 0 && n <= (k <= 32 ? 1LL : 2LL) * num_sms() * FAST_SMALL_WARPS && k <= 64) {
       // fast tier over all columns, then the general kernel (the larger of its tiers) over the columns it handed on
       rc = launch_fast_small(tier_params(0, 0, false, true, false), n, st);
       if (rc) return rc;
