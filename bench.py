@@ -521,7 +521,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg5", choices=sorted(WORKLOADS) + ["next"],
+                    help="cfgN: BASELINE.json configs; next: per-kernel lines of the K1 gathers, K5 and the SURVEY 8(f) rows (bench_next.py)")
+    ap.add_argument("--quick", action="store_true", help="--workload next: smaller shapes")
+    ap.add_argument("--only", default="", help="--workload next: comma-separated kernel names")
     ap.add_argument("--cpu-cols", type=int, default=0)
     ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes of the CPU baseline (default: all host cores)")
     ap.add_argument("--batch", type=int, default=0, help="override the global minibatch size (analysis only; the line says so)")
@@ -530,6 +533,9 @@ def main():
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the fused step as a CUDA graph (auto: the small workloads cfg1..cfg4 on one GPU)")
     args = ap.parse_args()
+    if args.workload == "next":
+        import bench_next
+        return bench_next.main((["--quick"] if args.quick else []) + (["--only", args.only] if args.only else []))
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "ours" and args.workload != "cfg5" and args.graph != "off" and args.warmup < 5:

@@ -45,8 +45,14 @@ def to_sample_major(X, dtype, dev):
 
 
 def from_sample_major(Ht):
-    """device (n x k) -> numpy float64 (k x n)."""
-    return Ht.detach().to(torch.float64).cpu().numpy().T.copy()
+    """device (n x k) -> numpy float64 (k x n); transposed + widened on the device (K1 transpose), one D2H copy."""
+    Ht = Ht.detach()
+    n, k = Ht.shape
+    if n == 0 or k == 0 or not Ht.is_cuda or Ht.dtype not in (torch.float32, torch.float64):
+        return Ht.to(torch.float64).cpu().numpy().T.copy()
+    out = torch.empty(k, n, dtype=torch.float64, device=Ht.device)
+    _lib.transpose(Ht.contiguous(), out)
+    return out.cpu().numpy()
 
 
 def to_device(M, dtype, dev):

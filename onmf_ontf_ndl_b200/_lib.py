@@ -187,7 +187,9 @@ def _req(t, name, dtype=None):
 # ---- thin wrappers (shapes documented in include/onmf_b200.h) --------------------------------
 
 def gather_patches(img, coords, p, out, stream=None):
-    _req(img, "img"); _req(coords, "coords", torch.int32); _req(out, "out", img.dtype)
+    _req(img, "img"); _req(coords, "coords", torch.int32)
+    if not out.is_cuda or out.dtype != img.dtype or out.dim() != 2 or (out.shape[0] > 1 and out.stride(1) != 1):
+        raise OnmfKernelError("out must be a CUDA (n x d) tensor of the image's dtype with unit column stride (rows may be pitched)")
     H, Wd = img.shape[0], img.shape[1]
     C = img.shape[2] if img.dim() == 3 else 1
     n = coords.shape[0]

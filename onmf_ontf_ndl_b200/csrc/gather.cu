@@ -36,6 +36,87 @@ __global__ void gather_patches_kernel(const T* __restrict__ img, int H, int Wd, 
   }
 }
 
+// Vector form (the default whenever a patch's feature count and the output pitch are multiples of 16 bytes): one thread per
+// 16 bytes of OUTPUT.  The output (n x d, every byte written once) is the only HBM stream of this kernel -- the image is read
+// n*d/(H*W) times over and stays in L1/L2 -- so the store side is what has to be coalesced: consecutive threads write
+// consecutive 16-byte pieces of consecutive patches, while the source elements (arbitrary alignment: b*C is any integer)
+// are fetched as scalars through L1.  IdxT = 32-bit when n*d/V fits (a 64-bit division per thread costs more than the copy).
+template <typename T, int V, typename IdxT>
+__global__ void __launch_bounds__(256) gather_patches_vec_kernel(const T* __restrict__ img, int H, int Wd, int C,
+                                                                 const int32_t* __restrict__ coords, long long n, int p,
+                                                                 T* __restrict__ Xt, long long ld, int dv) {
+  struct __align__(16) Vec { T v[V]; };
+  const int run = p * C;
+  const IdxT total = (IdxT)n * (IdxT)dv;
+  const IdxT stride = (IdxT)gridDim.x * blockDim.x;
+  auto fetch = [&](IdxT g, Vec& out) -> T* {
+    const IdxT j = g / (IdxT)dv;
+    const int e0 = (int)(g - j * (IdxT)dv) * V;
+    const int2 ab = reinterpret_cast<const int2*>(coords)[j];
+    const int a = ab.x, b = ab.y;
+    if (a < 0 || b < 0 || a > H - p || b > Wd - p) {          // corner outside the image: poison, never read out of bounds
+#pragma unroll
+      for (int t = 0; t < V; ++t) out.v[t] = nan_of<T>();
+    } else {
+      int r = e0 / run, c = e0 - r * run;
+      const T* src = img + ((size_t)(a + r) * Wd + b) * C + c;
+#pragma unroll
+      for (int t = 0; t < V; ++t) {
+        out.v[t] = __ldg(src);
+        ++src;
+        if (++c == run) {                                    // next patch row (the pointer past the last row is never read)
+          c = 0;
+          ++r;
+          src = img + ((size_t)(a + r) * Wd + b) * C;
+        }
+      }
+    }
+    return Xt + (size_t)j * ld + e0;
+  };
+  for (IdxT g = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+    Vec o;
+    T* dst = fetch(g, o);
+    *reinterpret_cast<Vec*>(dst) = o;
+  }
+}
+
+// Tiled form of the same copy (the default: d / V <= 1024 vectors per patch, image below 2^31 elements): blockDim.x = the
+// vectors of ONE patch, blockDim.y = patches per CTA.  A thread keeps its position inside the patch for the whole grid-stride
+// loop, so the two integer divisions and the row-crossing logic of the flat kernel (which made it issue-bound at 0.45 of the
+// HBM rate) are paid once per thread: the V source offsets relative to the patch corner are loop invariants, and a patch costs
+// one broadcast corner load, V scalar loads and one 16-byte store.  Linear thread order == output order, stores stay coalesced.
+template <typename T, int V>
+__global__ void __launch_bounds__(1024) gather_patches_tile_kernel(const T* __restrict__ img, int H, int Wd, int C,
+                                                                   const int32_t* __restrict__ coords, long long n, int p,
+                                                                   T* __restrict__ Xt, long long ld) {
+  struct __align__(16) Vec { T v[V]; };
+  const int run = p * C;
+  const int e0 = threadIdx.x * V;
+  int off[V];
+  {
+    int r = e0 / run, c = e0 - r * run;
+#pragma unroll
+    for (int t = 0; t < V; ++t) {
+      off[t] = r * Wd * C + c;
+      if (++c == run) { c = 0; ++r; }
+    }
+  }
+  const long long step = (long long)gridDim.x * blockDim.y;
+  for (long long j = (long long)blockIdx.x * blockDim.y + threadIdx.y; j < n; j += step) {
+    const int2 ab = __ldg(reinterpret_cast<const int2*>(coords) + j);
+    Vec out;
+    if (ab.x < 0 || ab.y < 0 || ab.x > H - p || ab.y > Wd - p) {
+#pragma unroll
+      for (int t = 0; t < V; ++t) out.v[t] = nan_of<T>();
+    } else {
+      const T* src = img + ((size_t)ab.x * Wd + ab.y) * C;
+#pragma unroll
+      for (int t = 0; t < V; ++t) out.v[t] = __ldg(src + off[t]);
+    }
+    *reinterpret_cast<Vec*>(Xt + (size_t)j * ld + e0) = out;
+  }
+}
+
 template <typename T>
 __global__ void gather_rows_kernel(const T* __restrict__ pool, long long n_pool, int d, const long long* __restrict__ idx,
                                    long long n, T* __restrict__ Xt) {
@@ -67,6 +148,41 @@ __global__ void transpose_kernel(const TI* __restrict__ src, long long rows, lon
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     long long c = c0 + i, r = r0 + threadIdx.x;
     if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+// Vector form: 64 x 64 tiles, 256 threads, four elements per access on both sides (16 bytes of fp32, 32 of fp64) -- used when
+// rows and cols are multiples of 4 and both pointers are 32-byte aligned.  The 32 x 32 scalar kernel above reached 0.44-0.55
+// of the HBM copy rate at the matricization shapes (profiles/r2_next_rows.md); this one moves 4x the bytes per instruction.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) transpose64_kernel(const TI* __restrict__ src, long long rows, long long cols,
+                                                          TO* __restrict__ dst) {
+  struct __align__(sizeof(TI) * 4) VI { TI v[4]; };
+  struct __align__(sizeof(TO) * 4) VO { TO v[4]; };
+  __shared__ TO tile[64][65];
+  const long long c0 = (long long)blockIdx.x * 64, r0 = (long long)blockIdx.y * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // 16 four-element vectors across, 16 lines down
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = ty + 16 * i;
+    const long long r = r0 + rr, c = c0 + 4 * tx;
+    if (r < rows && c < cols) {                                    // cols % 4 == 0: a vector is inside or outside as a whole
+      const VI v = *reinterpret_cast<const VI*>(src + (size_t)r * cols + c);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tile[rr][4 * tx + e] = (TO)v.v[e];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cc = ty + 16 * i;
+    const long long c = c0 + cc, r = r0 + 4 * tx;
+    if (c < cols && r < rows) {
+      VO v;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v.v[e] = tile[4 * tx + e][cc];
+      *reinterpret_cast<VO*>(dst + (size_t)c * rows + r) = v;
+    }
   }
 }
 
@@ -197,6 +313,67 @@ __global__ void pgd_columns_kernel(const T* __restrict__ G, const T* __restrict_
   }
 }
 
+// The same per-sample coder for small dictionaries (k <= 32) on LARGE batches -- image reconstruction codes every grid patch
+// of an image in one call (reconstruct.py: 252,004 patches of a 512 x 512 image at k = 25): ONE THREAD per sample.  The
+// warp-per-sample kernel above spends ~100 warp-instructions (five shuffles, the lane select, a division) on a Gauss-Seidel
+// coordinate whose arithmetic is k multiply-adds; here the code vector lives in the thread's registers (KP = k rounded up to
+// a multiple of 4, fully unrolled), the zero-padded Gram is read from shared memory at warp-uniform addresses (broadcast,
+// 16 bytes per load) and the per-coordinate step 1 / (G_qq + 1) is tabulated once per CTA.  Same iteration, same stopping
+// test; the dot products are summed in index order instead of the butterfly order, so results agree with the kernel above to
+// rounding (fp64: ~1e-16), not bit for bit.  Rows of Ct / Ht are read and written directly: the 32 rows of a warp are one
+// contiguous block, every line is used completely through L1.
+template <typename T, int KP>
+__global__ void __launch_bounds__(128) pgd_columns_tps_kernel(const T* __restrict__ G, const T* __restrict__ Ct, long long n, int k,
+                                                             T alpha, int sub_iter, T stopping_diff, T* __restrict__ Ht) {
+  __shared__ __align__(16) T Gs[KP * KP];
+  __shared__ T inv[KP];
+  for (int i = threadIdx.x; i < KP * KP; i += blockDim.x) {
+    const int q = i / KP, c = i - q * KP;
+    Gs[i] = (q < k && c < k) ? G[q * k + c] : T(0);
+  }
+  for (int q = threadIdx.x; q < KP; q += blockDim.x) inv[q] = q < k ? T(1) / (G[q * k + q] + T(1)) : T(0);
+  __syncthreads();
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  T h[KP], c[KP];
+#pragma unroll
+  for (int i = 0; i < KP; ++i) {
+    h[i] = i < k ? Ht[(size_t)j * k + i] : T(0);
+    c[i] = i < k ? Ct[(size_t)j * k + i] - alpha : T(0);       // grad = G[q,:] h - (c_q - alpha)
+  }
+  T dist = T(1);
+  for (int it = 0; it < sub_iter && dist > stopping_diff; ++it) {
+    const T rscale = T(1) / (T)sqrt((double)it + 10.0);
+    T num = T(0), den = T(0);
+    int off = 0;
+    asm volatile("" : "+r"(off));              // the Gram is re-read every sweep (hoisting k^2 loads out of the loop spills)
+    const T* Gp = Gs + off;
+    const T* ip = inv + off;
+#pragma unroll
+    for (int q = 0; q < KP; ++q) {
+      T p0 = T(0), p1 = T(0), p2 = T(0), p3 = T(0);
+#pragma unroll
+      for (int i = 0; i < KP; i += 4) {
+        p0 += Gp[q * KP + i] * h[i];
+        p1 += Gp[q * KP + i + 1] * h[i + 1];
+        p2 += Gp[q * KP + i + 2] * h[i + 2];
+        p3 += Gp[q * KP + i + 3] * h[i + 3];
+      }
+      const T grad = ((p0 + p1) + (p2 + p3)) - c[q];
+      T v = h[q] - (rscale * ip[q]) * grad;
+      v = (q < k && v > T(0)) ? v : T(0);
+      const T dv = v - h[q];
+      num += dv * dv;
+      den += h[q] * h[q];
+      h[q] = v;
+    }
+    dist = sqrt(num) / sqrt(den);
+  }
+#pragma unroll
+  for (int i = 0; i < KP; ++i)
+    if (i < k) Ht[(size_t)j * k + i] = h[i];
+}
+
 // Overlap-averaged canvas from per-patch reconstructions (the running mean of image_reconstruction.py:389-392 and
 // sklearn's reconstruct_from_patches_2d): patches of size p x p (x C channels) with top-left corners on the grid
 // (gy*stride, gx*stride), gy < ny, gx < nx, stored row-major as R[(gy*nx + gx), (r*p + c)*C + ch].
@@ -266,6 +443,13 @@ static int pgd_t(const T* G, const T* Ct, long long n, int k, double alpha, int 
 
 template <typename TI, typename TO>
 static int transpose_t(const void* src, long long rows, long long cols, void* dst, cudaStream_t st) {
+  if (rows % 4 == 0 && cols % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 31) == 0 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0 &&
+      cdiv<long long>(rows, 64) <= 65535) {
+    dim3 grid64((unsigned)cdiv<long long>(cols, 64), (unsigned)cdiv<long long>(rows, 64));
+    transpose64_kernel<TI, TO><<<grid64, 256, 0, st>>>((const TI*)src, rows, cols, (TO*)dst);
+    ONMF_LAUNCH_CHECK("transpose64_kernel");
+    return ONMF_OK;
+  }
   dim3 block(32, 8);
   dim3 grid((unsigned)cdiv<long long>(cols, 32), (unsigned)cdiv<long long>(rows, 32));
   if (grid.y > 65535) return fail(ONMF_E_UNSUPPORTED, "transpose: more than 2^21 rows; transpose the other way");
@@ -285,6 +469,41 @@ extern "C" int onmf_gather_patches(int dtype, const void* img, int H, int Wd, in
   if (n == 0) return ONMF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int threads = 256;
+  {
+    // vector path: 16 bytes of output per thread
+    const int V = dtype == ONMF_F32 ? 4 : 2;
+    const long long d = (long long)p * p * C;
+    if ((dtype == ONMF_F32 || dtype == ONMF_F64) && d % V == 0 && ld % V == 0 && (reinterpret_cast<uintptr_t>(Xt) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(coords) & 7) == 0) {
+      const int dv = (int)(d / V);
+      if (dv <= 1024 && (long long)H * Wd * C < (1LL << 31)) {
+        int py = 256 / dv;                                   // patches per CTA: about 256 threads
+        if (py < 1) py = 1;
+        dim3 block((unsigned)dv, (unsigned)py);
+        long long gq = cdiv<long long>(n, py);
+        const long long capq = (long long)num_sms() * (2048 / (dv * py)) * 4;
+        const int gridq = (int)(gq > capq ? capq : gq);
+        if (dtype == ONMF_F32) gather_patches_tile_kernel<float, 4><<<gridq, block, 0, st>>>((const float*)img, H, Wd, C, coords, n, p, (float*)Xt, ld);
+        else gather_patches_tile_kernel<double, 2><<<gridq, block, 0, st>>>((const double*)img, H, Wd, C, coords, n, p, (double*)Xt, ld);
+        ONMF_LAUNCH_CHECK("gather_patches_tile_kernel");
+        return ONMF_OK;
+      }
+      const long long total = n * dv;
+      long long g = cdiv<long long>(total, threads);
+      const long long cap = 16LL * num_sms();
+      const int grid = (int)(g > cap ? cap : g);
+      const bool small = total + (long long)grid * threads < (1LL << 31);
+      if (dtype == ONMF_F32) {
+        if (small) gather_patches_vec_kernel<float, 4, unsigned><<<grid, threads, 0, st>>>((const float*)img, H, Wd, C, coords, n, p, (float*)Xt, ld, dv);
+        else gather_patches_vec_kernel<float, 4, unsigned long long><<<grid, threads, 0, st>>>((const float*)img, H, Wd, C, coords, n, p, (float*)Xt, ld, dv);
+      } else {
+        if (small) gather_patches_vec_kernel<double, 2, unsigned><<<grid, threads, 0, st>>>((const double*)img, H, Wd, C, coords, n, p, (double*)Xt, ld, dv);
+        else gather_patches_vec_kernel<double, 2, unsigned long long><<<grid, threads, 0, st>>>((const double*)img, H, Wd, C, coords, n, p, (double*)Xt, ld, dv);
+      }
+      ONMF_LAUNCH_CHECK("gather_patches_vec_kernel");
+      return ONMF_OK;
+    }
+  }
   long long warps = n * p;
   int grid = (int)cdiv<long long>(warps * 32, threads);
   if (grid > 8 * num_sms()) grid = 8 * num_sms();
@@ -352,6 +571,26 @@ extern "C" int onmf_pgd_code_columns(int dtype, const void* G, const void* Ct, i
   size_t smem = (size_t)k * k * tsz;
   const int gsm = smem <= (size_t)max_smem_optin() ? 1 : 0;
   if (!gsm) smem = 0;
+  if (k <= 32 && n >= 16LL * num_sms()) {
+    // large batch, small dictionary: one thread per sample (pgd_columns_tps_kernel)
+    const unsigned g = (unsigned)cdiv<long long>(n, 128);
+#define ONMF_TPS(TT, KP) pgd_columns_tps_kernel<TT, KP><<<g, 128, 0, st>>>((const TT*)G, (const TT*)Ct, n, k, (TT)alpha, sub_iter, (TT)stopping_diff, (TT*)Ht)
+#define ONMF_TPS_K(TT)                   \
+  if (k <= 8) ONMF_TPS(TT, 8);           \
+  else if (k <= 12) ONMF_TPS(TT, 12);    \
+  else if (k <= 16) ONMF_TPS(TT, 16);    \
+  else if (k <= 20) ONMF_TPS(TT, 20);    \
+  else if (k <= 24) ONMF_TPS(TT, 24);    \
+  else if (k <= 28) ONMF_TPS(TT, 28);    \
+  else ONMF_TPS(TT, 32);
+    if (dtype == ONMF_F32) { ONMF_TPS_K(float) }
+    else if (dtype == ONMF_F64) { ONMF_TPS_K(double) }
+    else return fail(ONMF_E_ARG, "pgd_code_columns: bad dtype");
+#undef ONMF_TPS_K
+#undef ONMF_TPS
+    ONMF_LAUNCH_CHECK("pgd_columns_tps_kernel");
+    return ONMF_OK;
+  }
   int threads = 256;
   int grid = (int)cdiv<long long>(n * 32, threads);
   if (grid > 4 * num_sms()) grid = 4 * num_sms();

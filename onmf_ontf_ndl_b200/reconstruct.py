@@ -58,11 +58,13 @@ def reconstruct_image(A, W, patch_size, recons_resolution=1, alpha=1, sub_iter=1
         Ht = eng.sparse_code(Xt, Wd, alpha=alpha).clone()                    # K2 + K3
     elif coder == "pgd":
         if H0 is None:
-            H0 = np.random.rand(n, r).T                                      # same stream as n calls of np.random.rand(r, 1)
-        H0 = np.asarray(H0, dtype=np.float64)
-        if H0.shape != (r, n):
-            raise ValueError("H0 must have shape (r, n_patches) = (%d, %d)" % (r, n))
-        Ht = _host.to_device(np.ascontiguousarray(H0.T), dtype, dev)
+            # same stream as n calls of np.random.rand(r, 1); already sample-major
+            Ht = _host.to_device(np.random.rand(n, r), dtype, dev)
+        else:
+            H0 = np.asarray(H0, dtype=np.float64)
+            if H0.shape != (r, n):
+                raise ValueError("H0 must have shape (r, n_patches) = (%d, %d)" % (r, n))
+            Ht = _host.to_sample_major(H0, dtype, dev)                        # uploaded as it is, transposed on the device
         G = torch.empty(r, r, dtype=dtype, device=dev)
         Ct = torch.empty(n, r, dtype=dtype, device=dev)
         _lib.gram(Wd, G)
@@ -122,16 +124,27 @@ def reconstruct_network(G, W, embs, alpha=0, precision=None):
     R = torch.empty(n, d, dtype=dtype, device=dev)
     if n:
         _lib.cov(Ht, Wt, R)                                                                          # patch_recons rows
-    cap = 1
-    while cap < 2 * max(n * d, 1) + 2:
+    # Table size: a table of 2 * n * k^2 slots always suffices (every entry a distinct pair), but consecutive states of the
+    # Glauber walk differ in one node, so a trajectory visits about n * (2k - 1) distinct directed pairs: start there (20 bytes
+    # per slot -- the worst-case table of a 10^6-state trajectory at k = 21 would be 20 GB) and grow on the kernel's
+    # "table full" report.
+    worst = 2 * max(n * d, 1) + 2
+    cap = 1024
+    while cap < min(worst, 2 * n * 4 * kk + 2):
         cap *= 2
-    keys = torch.full((cap,), -1, dtype=torch.int64, device=dev)
-    sums = torch.zeros(cap, dtype=torch.float64, device=dev)
-    cnts = torch.zeros(cap, dtype=torch.int32, device=dev)
-    failed = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.edge_scatter_add(R, e, keys, sums, cnts, failed)
-    if int(failed.item()):
-        raise _lib.OnmfKernelError("edge_scatter_add could not place %d entries" % int(failed.item()))
+    while True:
+        keys = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+        sums = torch.zeros(cap, dtype=torch.float64, device=dev)
+        cnts = torch.zeros(cap, dtype=torch.int32, device=dev)
+        failed = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.edge_scatter_add(R, e, keys, sums, cnts, failed)
+        nf = int(failed.item())
+        if nf == 0:
+            break
+        if cap >= worst:
+            raise _lib.OnmfKernelError("edge_scatter_add could not place %d entries" % nf)
+        del keys, sums, cnts
+        cap *= 4
     used = torch.nonzero(cnts > 0).flatten()
     kz = keys[used].cpu().numpy().astype(np.uint64)
     sm = sums[used].cpu().numpy()

@@ -719,6 +719,18 @@ def test_batched_network_reconstruction_matches_reference(golden_dir):
     # empty trajectory
     p0, w0, c0 = reconstruct_network(G, g["W"], np.empty((0, 6), dtype=np.int64))
     assert len(p0) == 0 and len(w0) == 0
+    # unrelated states (every directed pair distinct): the pair table starts at the size a Glauber walk needs and grows
+    rng = np.random.default_rng(3)
+    G2 = nx.gnm_random_graph(500, 6000, seed=1)
+    kk, r, n = 21, 5, 100
+    embs = rng.integers(0, 500, size=(n, kk))
+    W2 = rng.random((kk * kk, r)); W2 /= np.linalg.norm(W2, axis=0)
+    pairs2, weight2, count2 = reconstruct_network(G2, W2, embs, alpha=0, precision="fp64")
+    adj = {u: set(G2.neighbors(u)) for u in G2.nodes()}
+    wref, cref = O.reconstruct_network_loop(adj, W2, embs, alpha=0.0)
+    assert len(pairs2) == len(wref) > 2 * n * 4 * kk
+    got = {(int(a), int(b)): (w, c) for (a, b), w, c in zip(pairs2.tolist(), weight2.tolist(), count2.tolist())}
+    assert all(got[key][1] == cref[key] and abs(got[key][0] - wref[key]) < 1e-9 for key in wref)
 
 
 # ---------------------------------------------------------------------------------------------- robustness of the gathers / large shapes
@@ -1033,3 +1045,73 @@ def test_spectral_norm_kernel():
             got = float(out[0])
             tol = 2e-5 if dt_ == torch.float64 else 1e-4
             assert abs(got - ref) <= tol * max(ref, 1e-300) + (0 if ref > 0 else 1e-300), (n, k, dt_, got, ref)
+
+
+# ---------------------------------------------------------------------------------------------- K1 vector forms, batched PGD
+def test_vector_gathers_equal_scalar_forms():
+    """The 16-byte forms of the patch gather / transpose (taken whenever shapes and alignment allow) move the same bytes
+    as the scalar kernels: bit-equal to plain indexing, for fp32 and fp64, gray and colour, incl. poisoned patches."""
+    g = torch.Generator(device=dev()); g.manual_seed(5)
+    for dt in (torch.float32, torch.float64):
+        # (the last two shapes have more than 1024 sixteen-byte pieces per patch: the flat vector kernel instead of the tiled one)
+        for (H, Wd, C, p) in ((40, 37, 1, 10), (33, 41, 3, 10), (64, 64, 1, 20), (19, 23, 3, 3), (50, 50, 2, 7), (16, 16, 1, 16),
+                              (40, 40, 1, 32), (70, 70, 1, 46), (80, 80, 1, 66)):
+            img = torch.rand(H, Wd, C, dtype=dt, device=dev(), generator=g)
+            n = 777
+            co = torch.stack([torch.randint(0, H - p + 1, (n,), device=dev(), generator=g),
+                              torch.randint(0, Wd - p + 1, (n,), device=dev(), generator=g)], 1).to(torch.int32)
+            co[5] = torch.tensor([H - p + 1, 0]); co[6] = torch.tensor([-1, 0]); co[7] = torch.tensor([0, Wd - p + 1])
+            co = co.contiguous()
+            d = p * p * C
+            for ld in (d, d + 4, d + 1):                       # pitch d + 1 breaks the 16-byte pitch -> scalar kernel
+                buf = torch.zeros(n, ld, dtype=dt, device=dev())
+                out = buf[:, :d]
+                _lib.gather_patches(img, co, p, out)
+                ok = torch.ones(n, dtype=torch.bool, device=dev()); ok[5:8] = False
+                ii = torch.nonzero(ok).flatten()
+                a, b = co[ii, 0].long(), co[ii, 1].long()
+                rr = torch.arange(p, device=dev())
+                ref = img[(a[:, None, None] + rr[None, :, None]), (b[:, None, None] + rr[None, None, :])].reshape(len(ii), d)
+                assert torch.equal(out[ii], ref), (dt, H, Wd, C, p, ld)
+                assert torch.isnan(out[5:8]).all()
+                if ld > d:
+                    assert float(buf[:, d:].abs().max()) == 0.0   # nothing written beyond a patch's d features
+    for (r, c) in ((64, 128), (68, 132), (4, 4), (1024, 300), (300, 1024), (35, 77), (36, 77), (200, 8)):
+        for ti in (torch.float32, torch.float64):
+            for to in (torch.float32, torch.float64):
+                src = torch.rand(r, c, dtype=ti, device=dev(), generator=g)
+                dst = torch.empty(c, r, dtype=to, device=dev())
+                _lib.transpose(src, dst)
+                assert torch.equal(dst, src.T.to(to)), (r, c, ti, to)
+
+
+@pytest.mark.parametrize("k", [5, 12, 25, 32])
+def test_thread_per_sample_pgd_equals_warp_per_sample(k):
+    """pgd_code_columns takes one thread per sample for k <= 32 on large batches; same iteration and stopping test as the
+    warp-per-sample kernel (and the oracle's update_code_within_radius per column), sums in index order."""
+    rng = np.random.default_rng(k)
+    d, n = 40, 16 * 160 + 37                                    # above the 16 * SMs switch on a 148-SM part
+    W = rng.random((d, k)); W /= np.maximum(1.0, np.linalg.norm(W, axis=0))
+    X = rng.random((d, n)); H0 = rng.random((k, n))
+    H0[:, 3] = 0.0                                              # zero start: dist = x / 0 on the first sweep
+    for dt, tol in ((torch.float64, 1e-12), (torch.float32, 2e-5)):
+        Wd = tt(W, dt); Xt = tt(X.T, dt)
+        G = torch.empty(k, k, dtype=dt, device=dev()); Ct = torch.empty(n, k, dtype=dt, device=dev())
+        _lib.gram(Wd, G); _lib.cov(Xt, Wd, Ct)
+        for sub_iter, stop in ((10, 0.01), (3, 0.0), (25, 0.05)):
+            big = tt(H0.T, dt)
+            _lib.pgd_code_columns(G, Ct, 0.7, sub_iter, stop, big)                 # thread per sample
+            small = tt(H0.T, dt)
+            for lo in range(0, n, 500):                                            # chunks below the switch: warp per sample
+                _lib.pgd_code_columns(G, Ct[lo:lo + 500], 0.7, sub_iter, stop, small[lo:lo + 500])
+            a, b = big.cpu().numpy().astype(np.float64), small.cpu().numpy().astype(np.float64)
+            fin = np.isfinite(b).all(axis=1)
+            assert np.array_equal(fin, np.isfinite(a).all(axis=1))
+            # a column whose stopping test sits within rounding of the threshold may take one sweep more or less
+            bad = np.linalg.norm(a[fin] - b[fin], axis=1) > tol * np.maximum(np.linalg.norm(b[fin], axis=1), 1e-30)
+            assert bad.sum() <= (0 if dt == torch.float64 else 2), (k, dt, sub_iter, int(bad.sum()))
+        if dt == torch.float64:
+            ref = np.stack([O.update_code_within_radius(X[:, j:j + 1], W, H0[:, j:j + 1].copy(), None, 0.7, 25, 0.05)[:, 0]
+                            for j in range(0, 64) if j != 3], 0)
+            got = np.delete(a[:64], 3, axis=0)
+            assert rel(got, ref) < 1e-10
