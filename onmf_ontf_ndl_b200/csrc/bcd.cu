@@ -147,6 +147,123 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
   }
 }
 
+// Small dictionaries (d <= 1024 rows, W and A together within one CTA's shared memory: BASELINE configs 1-4, every per-patch
+// driver call): ONE CTA, one thread per row, no cluster and no global memory inside the atom loop.  The cluster kernel above
+// pays ~2.3 us per atom even as a cluster of one (barrier.cluster + the L2 latency of the prefetched column of A on the
+// k-step chain; bench.py --workload next: 57 us at d=100, k=25 -- the longest kernel of a cfg1 step); here W (row-padded to
+// an odd pitch: conflict-free), A and the warp partials live in shared memory, B[j, row] rides a four-deep register ring,
+// and an atom costs k multiply-adds per thread (four fp32 chains, combined and differenced with B in FP64 like above), one
+// warp reduction and ONE __syncthreads (the partial-sum buffer alternates with the atom's parity).  Partials are summed in
+// warp order by every thread: deterministic, bit-identical on every GPU of a data-parallel run.
+template <typename T>
+struct BcdVec;
+template <>
+struct BcdVec<float> {
+  static constexpr int N = 4;
+  typedef float4 type;
+  static __device__ __forceinline__ void fma4(const float4& w, const float4& a, float (&acc)[4], int) {
+    acc[0] += w.x * a.x; acc[1] += w.y * a.y; acc[2] += w.z * a.z; acc[3] += w.w * a.w;
+  }
+};
+template <>
+struct BcdVec<double> {
+  static constexpr int N = 2;
+  typedef double2 type;
+  static __device__ __forceinline__ void fma4(const double2& w, const double2& a, double (&acc)[4], int c) {
+    if (c & 1) { acc[2] += w.x * a.x; acc[3] += w.y * a.y; }
+    else { acc[0] += w.x * a.x; acc[1] += w.y * a.y; }
+  }
+};
+
+// shared-memory pitches of bcd_small_kernel: 16-byte chunks; an ODD number of chunks per row of W makes the 16-byte row
+// reads of eight consecutive threads (one shared-memory wavefront) hit eight different bank groups
+template <typename T>
+static inline int bcd_small_ks(int k) {
+  const int V = 16 / (int)sizeof(T);
+  int ks = round_up(k, V);
+  if (((ks / V) & 1) == 0) ks += V;
+  return ks;
+}
+template <typename T>
+static inline int bcd_small_ka(int k) { return round_up(k, 16 / (int)sizeof(T)); }
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 1) bcd_small_kernel(const T* __restrict__ Win, const T* __restrict__ A, const T* __restrict__ B,
+                                                            T* __restrict__ Wout, int d, int k, int ks, int ka) {
+  typedef typename BcdVec<T>::type V;
+  constexpr int VN = BcdVec<T>::N;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Ws = reinterpret_cast<T*>(smem_raw);                  // d x ks, zero beyond column k
+  T* At = Ws + (size_t)d * ks;                             // k x ka: At[j][q] = A[q][j] (column j of A, contiguous), zero padded
+  T* part = At + (size_t)k * ka;                           // 2 x 32
+  double* cjs = reinterpret_cast<double*>(part + 64);      // k: 1 / (A_jj + 1), off the atom chain (an FP64 division each)
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  for (int j = tid; j < k; j += nthr) cjs[j] = 1.0 / ((double)A[(size_t)j * k + j] + 1.0);
+  for (int idx = tid; idx < d * ks; idx += nthr) {
+    const int r = idx / ks, q = idx - r * ks;
+    Ws[idx] = q < k ? Win[(size_t)r * k + q] : T(0);
+  }
+  for (int idx = tid; idx < k * ka; idx += nthr) {
+    const int j = idx / ka, q = idx - j * ka;
+    At[idx] = q < k ? A[(size_t)q * k + j] : T(0);
+  }
+  const bool has_row = tid < d;
+  T bq[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) bq[s] = (has_row && s < k) ? B[(size_t)s * d + tid] : T(0);
+  __syncthreads();
+  T* wrow = Ws + (size_t)(has_row ? tid : 0) * ks;
+  const int nch = ka / VN;
+  for (int j0 = 0; j0 < k; j0 += 4) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int j = j0 + s;
+      if (j < k) {                                         // (uniform)
+        const int par = j & 1;
+        T wnew = T(0);
+        if (has_row) {
+          T acc[4] = {T(0), T(0), T(0), T(0)};
+          const V* wv = reinterpret_cast<const V*>(wrow);
+          const V* av = reinterpret_cast<const V*>(At + (size_t)j * ka);
+#pragma unroll 4
+          for (int c = 0; c < nch; ++c) BcdVec<T>::fma4(wv[c], av[c], acc, c);
+          const double dot = ((double)acc[0] + (double)acc[1]) + ((double)acc[2] + (double)acc[3]);
+          const double cj = cjs[j];
+          const double v = (double)wrow[j] - cj * (dot - (double)bq[s]);
+          wnew = v > 0.0 ? (T)v : T(0);
+          bq[s] = (j + 4 < k) ? B[(size_t)(j + 4) * d + tid] : T(0);
+        }
+        T sq = wnew * wnew;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        if (lane == 0) part[par * 32 + warp] = sq;
+        __syncthreads();
+        T tot = T(0);
+        for (int w = 0; w < nwarp; ++w) tot += part[par * 32 + w];
+        const T nrm = sqrt(tot);
+        const T sc = T(1) / (nrm > T(1) ? nrm : T(1));
+        if (has_row) wrow[j] = sc * wnew;
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < d * k; idx += nthr) {
+    const int r = idx / k, q = idx - r * k;
+    Wout[idx] = Ws[(size_t)r * ks + q];
+  }
+}
+
+template <typename T>
+static size_t bcd_small_smem(int d, int k) {
+  return ((size_t)d * bcd_small_ks<T>(k) + (size_t)k * bcd_small_ka<T>(k) + 64) * sizeof(T) + (size_t)k * sizeof(double) + 8;
+}
+
+template <typename T>
+static bool bcd_small_fits(int d, int k) {
+  static const int off = [] { const char* e = getenv("ONMF_BCD_SMALL"); return (e && atoi(e) == 0) ? 1 : 0; }();   // (A/B runs)
+  return !off && d <= 1024 && bcd_small_smem<T>(d, k) <= (size_t)max_smem_optin() - 1024;
+}
+
 // Fallback for dictionaries that do not fit one cluster's shared memory (d*k beyond ~0.9 M fp32 / 0.45 M fp64 entries, e.g.
 // joint unfoldings of large tensors): a cooperative grid keeps W in global memory (L2 resident), every CTA owns a row
 // slab -- rows are only ever read and written by their owner, the sweep is row-separable -- and the column norm is a
@@ -244,6 +361,14 @@ static bool cluster_fits(int d, int k) {
 
 template <typename T>
 static int update_dict_t(const T* Win, const T* A, const T* B, int d, int k, T* Wout, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (bcd_small_fits<T>(d, k)) {
+    const size_t smem = bcd_small_smem<T>(d, k);
+    auto kern = bcd_small_kernel<T>;
+    ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, round_up(d, 32), smem, st>>>(Win, A, B, Wout, d, k, bcd_small_ks<T>(k), bcd_small_ka<T>(k));
+    ONMF_LAUNCH_CHECK("bcd_small_kernel");
+    return ONMF_OK;
+  }
   if (!cluster_fits<T>(d, k)) return update_dict_global_t<T>(Win, A, B, d, k, Wout, ws, ws_bytes, st);
   const size_t smem_cap = (size_t)max_smem_optin() - 1024;
   // smallest power-of-two cluster whose slabs fit; prefer <= 128 rows per CTA so several lanes share a row

@@ -116,7 +116,7 @@ class Online_NMF():
             return eng.sparse_code(Xt, Wd, alpha=self._alpha())
         n, r = Xt.shape[0], Wd.shape[1]
         H0 = np.random.rand(r, n)                              # src/onmf.py:245-246 (global host RNG)
-        Ht = _host.to_device(np.ascontiguousarray(H0.T), self._dtype, Xt.device)
+        Ht = _host.to_sample_major(H0, self._dtype, Xt.device)    # uploaded as drawn, transposed on the device
         return _pgd_device(Xt, Wd, Ht, self._alpha(), 10, 0.01)   # src/onmf.py:87
 
     def sparse_code(self, X, W):

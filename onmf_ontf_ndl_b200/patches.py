@@ -39,6 +39,21 @@ def gather_patches(img, coords, patch_size, precision=None, device=False):
     return out if device else _host.from_sample_major(out)
 
 
+def extract_patches_2d(img, patch_size, precision=None, device=False):
+    """ALL patches of an image in sklearn's order -- the data matrix the drivers build for reconstruction with
+    `extract_patches_2d(data, (k, k)).reshape(N, -1).T` (image_reconstruction.py:163-166, ising_reconstruction.py:185-186):
+    corners (i, j), i in 0..H-k, j in 0..W-k (the last offset INCLUDED, unlike the random sampler), row-major.
+    Returns X (k*k*C, N) numpy float64, or the sample-major device tensor (N x k*k*C) with device=True."""
+    A = np.asarray(img)
+    k = int(patch_size)
+    ny, nx = A.shape[0] - k + 1, A.shape[1] - k + 1
+    if ny <= 0 or nx <= 0:
+        raise ValueError("patch_size %d larger than the image %s" % (k, A.shape[:2]))
+    gy, gx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    coords = np.stack([gy.reshape(-1), gx.reshape(-1)], 1).astype(np.int32)
+    return gather_patches(A, coords, k, precision, device)
+
+
 def extract_random_patches(img, patch_size, num_patches, precision=None):
     """Drop-in for the drivers' extract_random_patches: gray -> (k*k, N); colour -> tensor (k*k, C, N)."""
     A = np.asarray(img)

@@ -84,6 +84,51 @@ def reconstruct_image(A, W, patch_size, recons_resolution=1, alpha=1, sub_iter=1
     return res
 
 
+def reconstruct_from_patches_2d(patches_or_W, image_size, code=None, precision=None):
+    """Overlap-averaged image from ALL its patches in sklearn's order -- the last two lines of the drivers' one-shot
+    reconstruction (image_reconstruction.py:351-354, image_reconstruction_tensor.py:280-283, ising_reconstruction.py:196-199):
+
+        patches_recons = np.dot(W, code).T.reshape(N, k, k);  img = reconstruct_from_patches_2d(patches_recons, dims)
+
+    Two call forms: `reconstruct_from_patches_2d(patches (N, k, k[, C]), (H, W))` -- sklearn's signature, the patches are
+    uploaded -- or `reconstruct_from_patches_2d(W (k*k*C, r), (H, W), code=code (r, N))`, which forms W code on the device
+    (K2-style product) and never materialises the N x k x k array on the host.  Both end in the deterministic gather-form
+    mean kernel onmf_patch_grid_mean.  Returns numpy float64 (H, W[, C])."""
+    dev = _host.device()
+    dtype = _host.torch_dtype(precision)
+    Hh, Ww = int(image_size[0]), int(image_size[1])
+    if code is None:
+        P = np.asarray(patches_or_W, dtype=np.float64)
+        if P.ndim not in (3, 4) or P.shape[1] != P.shape[2]:
+            raise ValueError("patches must have shape (N, k, k) or (N, k, k, C)")
+        n, k = P.shape[0], P.shape[1]
+        C = 1 if P.ndim == 3 else P.shape[3]
+        R = _host.to_device(P.reshape(n, -1), dtype, dev)
+    else:
+        W = np.asarray(patches_or_W, dtype=np.float64)
+        d, r = W.shape
+        C = int(image_size[2]) if len(image_size) > 2 else 1
+        k = int(round(np.sqrt(d // C)))
+        if k * k * C != d:
+            raise ValueError("dictionary rows %d are not patch_size^2 * channels (channels = %d)" % (d, C))
+        Ht = _host.to_sample_major(np.asarray(code, dtype=np.float64), dtype, dev)
+        n = Ht.shape[0]
+        if Ht.shape[1] != r:
+            raise ValueError("code must have shape (r, N) = (%d, N)" % r)
+        Wt = torch.empty(r, d, dtype=dtype, device=dev)
+        _lib.transpose(_host.to_device(W, dtype, dev), Wt)
+        R = torch.empty(n, d, dtype=dtype, device=dev)
+        if n:
+            _lib.cov(Ht, Wt, R)
+    ny, nx = Hh - k + 1, Ww - k + 1
+    if n != ny * nx:
+        raise ValueError("expected (H-k+1)*(W-k+1) = %d patches, got %d" % (ny * nx, n))
+    canvas = torch.empty(Hh, Ww, C, dtype=dtype, device=dev)
+    _lib.patch_grid_mean(R, ny, nx, k, 1, C, Hh, Ww, canvas)
+    out = canvas.cpu().numpy().astype(np.float64)
+    return out[:, :, 0] if (C == 1 and len(image_size) == 2) else out
+
+
 def reconstruct_network(G, W, embs, alpha=0, precision=None):
     """Batched form of Network_Reconstructor.reconstruct_network (network_reconstruction_nx.py:444-511).
 

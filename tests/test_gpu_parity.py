@@ -1115,3 +1115,28 @@ def test_thread_per_sample_pgd_equals_warp_per_sample(k):
                             for j in range(0, 64) if j != 3], 0)
             got = np.delete(a[:64], 3, axis=0)
             assert rel(got, ref) < 1e-10
+
+
+def test_sklearn_order_patch_helpers_one_shot_reconstruction():
+    """the drivers' one-shot reconstruction (image_reconstruction.py:335-357, ising_reconstruction.py:179-201):
+    extract_patches_2d(data, (k, k)) -> sparse_code -> np.dot(W, code).T -> reconstruct_from_patches_2d, against sklearn's
+    own two functions and numpy on the same code."""
+    from sklearn.feature_extraction.image import extract_patches_2d, reconstruct_from_patches_2d
+    from onmf_ontf_ndl_b200 import patches, reconstruct_from_patches_2d as recon_b200
+    rng = np.random.default_rng(11)
+    for shape, k in (((23, 31), 5), ((18, 20, 3), 4)):
+        img = rng.random(shape)
+        ref = extract_patches_2d(img, (k, k))
+        X = patches.extract_patches_2d(img, k, precision="fp64")
+        assert np.array_equal(X, ref.reshape(len(ref), -1).T)
+        r = 7
+        W = rng.random((X.shape[0], r)); W /= np.linalg.norm(W, axis=0)
+        code = Online_NMF(X, n_components=r, iterations=1, batch_size=10, alpha=0.1, precision="fp64").sparse_code(X, W)
+        assert rel(code, c_oracle.sparse_code(X, W, 0.1)) < 1e-9
+        pr = np.dot(W, code).T.reshape((len(ref),) + ref.shape[1:])
+        want = reconstruct_from_patches_2d(pr, shape)
+        assert rel(recon_b200(pr, shape[:2], precision="fp64"), want) < 1e-13
+        assert rel(recon_b200(W, shape, code=code, precision="fp64"), want) < 1e-13
+        assert rel(recon_b200(W, shape, code=code), want) < 1e-5
+    with pytest.raises(ValueError):
+        recon_b200(pr[:-1], shape[:2])
