@@ -345,6 +345,14 @@ class OnmfEngine:
 
     def _step(self, Xt, ref, t, codes, n):
         main, side = self.main, self.side
+        pend = getattr(self, "_d2h_pending", None)
+        if pend:
+            # step_host copy-backs run on their own stream: this step's dictionary update overwrites W_next -- wait for the
+            # copy that read that buffer (issued two steps ago, long finished)
+            ev = pend.pop(self.W_next.data_ptr(), None)
+            if ev is not None:
+                side.wait_event(ev)
+                main.wait_event(ev)
         presplit = Xt is None and ref is None
         self._reserve(max(n, 1))
         w = float(t) ** (-self.beta)
@@ -541,13 +549,28 @@ class OnmfEngine:
             Ht = self.step(buf, t)
         self._stage_ev[i].record(self.main)
         if W_out_host is not None:
-            with torch.cuda.stream(self.side):
+            # Copy-back on its own stream, after the whole step: on the side stream it sat between this step's blend and the
+            # next step's dictionary update, whose cluster then reached the GPU after the persistent coder had taken every
+            # SM and ran behind it instead of under it (N = 8, uint8 storage: 2.7 instead of 1.9 ms per step).
+            if getattr(self, "_d2h", None) is None:
+                self._d2h = torch.cuda.Stream(self.device)
+                self._d2h_events = {}
+                self._d2h_pending = {}
+            self._d2h.wait_stream(self.main)
+            self._d2h.wait_stream(self.side)
+            key = self.W.data_ptr()
+            done = self._d2h_events.setdefault(key, torch.cuda.Event())
+            with torch.cuda.stream(self._d2h):
                 W_out_host.copy_(self.W, non_blocking=True)     # self.W is the dictionary this step produced
+                done.record(self._d2h)
+            self._d2h_pending[key] = done
         return Ht
 
     def flush(self):
         """Make W, A, B (C) visible to the current stream / host."""
         self.main.wait_stream(self.side)
+        if getattr(self, "_d2h", None) is not None:
+            self.main.wait_stream(self._d2h)                     # (copy-backs of step_host)
 
     def state(self):
         self.flush()
