@@ -481,6 +481,20 @@ def test_patch_pipeline_helpers(golden_dir):
         for q in range(7):
             for r in range(7):
                 assert Xm[q * 7 + r, j] == float(G.has_edge(emb[j, q], emb[j, r]))
+    # tiled kernel (k*k <= 1024 entries per patch) and flat kernel (k = 33), fp64, node indices outside the graph -> 0
+    adj = {u: set(G.neighbors(u)) for u in G.nodes()}
+    for kk, nn in ((21, 97), (33, 41), (1, 5), (32, 33)):
+        emb = rng.integers(0, 60, size=(nn, kk))
+        for prec in ("fp64", "fp32"):
+            assert np.array_equal(patches.motif_patches(csr, emb, precision=prec), O.motif_patches(adj, emb))
+    e = torch.tensor([[0, -1, 60, 5, 5]], dtype=torch.int32, device=dev())
+    out = torch.full((1, 25), 7.0, device=dev())
+    _lib.motif_patches(torch.from_numpy(csr[0]).to(dev()), torch.from_numpy(csr[1]).to(dev()), e, out)
+    want = np.zeros((5, 5)); want[3, 3] = want[3, 4] = want[4, 3] = want[4, 4] = 1.0      # the self-loop at node 5
+    for a_, b_ in ((0, 3), (0, 4)):
+        want[a_, b_] = want[b_, a_] = float(G.has_edge(0, 5))
+    want[0, 0] = float(G.has_edge(0, 0))
+    assert np.array_equal(out.cpu().numpy().reshape(5, 5), want)
 
 
 def test_codes_large_active_sets_all_tiers():
