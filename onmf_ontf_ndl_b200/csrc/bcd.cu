@@ -22,9 +22,42 @@ namespace onmf {
 
 constexpr int BCD_MAX_CLUSTER = 16;
 
+// ---- point-to-point cluster signalling (PTX): a remote store into a peer CTA's shared memory followed by a release-arrive
+// on that peer's mbarrier; the peer's threads acquire-wait on their own mbarrier.  Lighter than barrier.cluster, which makes
+// every thread of every CTA of the cluster rendezvous once per atom.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster(uint32_t raddr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory"); }
+__device__ __forceinline__ void st_cluster(uint32_t raddr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory"); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t rmbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win, const T* __restrict__ A, const T* __restrict__ B,
-                           T* __restrict__ Wout, int d, int k, int rpc, int ks, int tpr) {
+                           T* __restrict__ Wout, int d, int k, int rpc, int ks, int tpr, int use_mbar) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int csize = (int)cluster.num_blocks();
@@ -33,7 +66,15 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
   T* aj = Ws + (size_t)rpc * ks;                           // 2 x k   (double-buffered column of A)
   T* warp_part = aj + 2 * k;                               // 32
   T* slots = warp_part + 32;                               // 2 x BCD_MAX_CLUSTER (written by peers)
+  // (Ws, aj, warp_part, slots hold rpc*ks + 2k + 64 elements; the mbarrier sits at the next 8-byte boundary)
+  const uint32_t mbar = (smem_u32(slots + 2 * BCD_MAX_CLUSTER) + 7u) & ~7u;
+  // step table 1 / (A_jj + 1), one FP64 division per atom per CTA instead of one per thread per atom
+  double* cs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(slots + 2 * BCD_MAX_CLUSTER) + 7u) & ~(uintptr_t)7u) + 2;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  if (use_mbar && tid == 0) {                              // two mbarriers, one per atom parity (see the push below)
+    mbar_init(mbar, (uint32_t)csize);
+    mbar_init(mbar + 8, (uint32_t)csize);
+  }
   const int row0 = rank * rpc;
   const int nrows = max(0, min(rpc, d - row0));
 
@@ -43,6 +84,7 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
     Ws[(size_t)r * ks + q] = (r < nrows) ? Win[(size_t)(row0 + r) * k + q] : T(0);
   }
   for (int q = tid; q < k; q += nthr) aj[q] = A[(size_t)q * k + 0];
+  for (int q = tid; q < k; q += nthr) cs[q] = 1.0 / ((double)A[(size_t)q * k + q] + 1.0);
   if (tid < 2 * BCD_MAX_CLUSTER) slots[tid] = T(0);
   cluster.sync();
 
@@ -89,6 +131,7 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
     return dsum;
   };
   double dot = team_dot(aj);                     // atom 0: nothing pending
+  double cj = cs[0];                             // step of atom j
 
   // Software pipeline over atoms.  Column j of W is final only after the cluster-wide norm of its new entries; column
   // j+1's dot product needs it in ONE term (W[row, j] A[j, j+1]).  So the norm reduction of atom j (DSMEM pushes + one
@@ -107,8 +150,7 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
     T wnew = T(0), wold = T(0);
     if (has_row) {
       wold = wrow[j];
-      const double c = 1.0 / ((double)a[j] + 1.0);
-      const double v = (double)wold - c * (dot - (double)bcur);
+      const double v = (double)wold - cj * (dot - (double)bcur);
       wnew = v > 0.0 ? (T)v : T(0);
     }
     bcur = bnext;
@@ -122,15 +164,29 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
       if (tid < csize) {
-        T* peer = cluster.map_shared_rank(slots, tid);
-        peer[par * BCD_MAX_CLUSTER + rank] = v;
+        if (use_mbar) {
+          // slot (par, rank) of peer `tid`, then a release-arrive on that peer's mbarrier of this parity (csize arrivals per
+          // atom).  Slot and mbarrier are reused at atom j+2: this CTA gets there only after it has seen the peer's arrival
+          // for atom j+1, which the peer issues after its own phase j has completed (every arrival of atom j delivered)
+          // and after all its threads have read the slots of atom j.  With ONE mbarrier an early arrival for atom j+1
+          // could be counted into a peer's still incomplete phase j.
+          st_cluster(mapa_u32(smem_u32(slots + par * BCD_MAX_CLUSTER + rank), (uint32_t)tid), v);
+          mbar_arrive_remote(mapa_u32(mbar + 8u * (uint32_t)par, (uint32_t)tid));
+        } else {
+          T* peer = cluster.map_shared_rank(slots, tid);
+          peer[par * BCD_MAX_CLUSTER + rank] = v;
+        }
       }
     }
-    cluster.barrier_arrive();                      // release: the pushes above are visible to whoever passes the wait
-    // ---- in the shadow of the reduction: atom j+1's dot product without its j-th term ----
+    if (!use_mbar) cluster.barrier_arrive();       // release: the pushes above are visible to whoever passes the wait
+    // ---- in the shadow of the reduction: atom j+1's dot product without its j-th term, and its step ----
     double pdot = 0.0;
-    if (j + 1 < k) pdot = team_dot(an);           // (the team's lanes share a warp: these reads precede the write below)
-    cluster.barrier_wait();
+    if (j + 1 < k) {
+      pdot = team_dot(an);                         // (the team's lanes share a warp: these reads precede the write below)
+      cj = cs[j + 1];
+    }
+    if (use_mbar) mbar_wait(mbar + 8u * (uint32_t)par, (uint32_t)((j >> 1) & 1));
+    else cluster.barrier_wait();
     T tot = T(0);
     for (int r = 0; r < csize; ++r) tot += slots[par * BCD_MAX_CLUSTER + r];
     const T nrm = sqrt(tot);
@@ -145,6 +201,7 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
     int r = idx / k, q = idx - r * k;
     Wout[(size_t)(row0 + r) * k + q] = Ws[(size_t)r * ks + q];
   }
+  cluster.sync();                                  // no CTA leaves while a peer could still address its shared memory
 }
 
 // Small dictionaries (d <= 1024 rows, W and A together within one CTA's shared memory: BASELINE configs 1-4, every per-patch
@@ -356,7 +413,7 @@ static bool cluster_fits(int d, int k) {
   while (tpr > 1 && rpc * tpr > 1024) tpr >>= 1;
   while (tpr > 1 && tpr * 2 > k) tpr >>= 1;
   const int ks = round_up(k, 32) + (tpr < 32 ? tpr : 1);
-  return ((size_t)rpc * ks + 2 * (size_t)k + 32 + 2 * BCD_MAX_CLUSTER) * sizeof(T) <= smem_cap;
+  return ((size_t)rpc * ks + 2 * (size_t)k + 32 + 2 * BCD_MAX_CLUSTER) * sizeof(T) + 32 + (size_t)k * 8 <= smem_cap;
 }
 
 template <typename T>
@@ -386,7 +443,7 @@ static int update_dict_t(const T* Win, const T* A, const T* B, int d, int k, T* 
       while (tpr_cap > 0 && tpr > tpr_cap) tpr >>= 1;
     }
     ks = round_up(k, 32) + (tpr < 32 ? tpr : 1);
-    smem = ((size_t)rpc * ks + 2 * (size_t)k + 32 + 2 * BCD_MAX_CLUSTER) * sizeof(T);
+    smem = ((size_t)rpc * ks + 2 * (size_t)k + 32 + 2 * BCD_MAX_CLUSTER) * sizeof(T) + 32 + (size_t)k * 8;
     bool fits = smem <= smem_cap && rpc <= 1024;
     if (fits && (rpc <= 128 || cs >= 8)) break;
     if (fits && cs * 2 > BCD_MAX_CLUSTER) break;
@@ -408,7 +465,8 @@ static int update_dict_t(const T* Win, const T* A, const T* B, int d, int k, T* 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ONMF_CUDA(cudaLaunchKernelEx(&cfg, kern, Win, A, B, Wout, d, k, rpc, ks, tpr));
+  static const int use_mbar = [] { const char* e = getenv("ONMF_BCD_MBAR"); return (e && atoi(e) == 0) ? 0 : 1; }();   // (A/B runs)
+  ONMF_CUDA(cudaLaunchKernelEx(&cfg, kern, Win, A, B, Wout, d, k, rpc, ks, tpr, use_mbar));
   ++g_launches;
   return ONMF_OK;
 }
