@@ -40,6 +40,17 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t rmbar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rmbar) : "memory");
 }
+// st.async: the value and the completion signal travel together (complete_tx on the destination CTA's mbarrier) -- no
+// release fence on the sender (ncu of the release-arrive form: `membar` among the top stall reasons of the atom chain)
+__device__ __forceinline__ void st_async_cluster(uint32_t raddr, float v, uint32_t rmbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void st_async_cluster(uint32_t raddr, double v, uint32_t rmbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr), "l"(__double_as_longlong(v)), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   uint32_t ok;
   do {
@@ -55,8 +66,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   } while (!ok);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win, const T* __restrict__ A, const T* __restrict__ B,
+// REGW (fp32, k % 4 == 0, 4 <= tpr, k <= 32 * tpr, <= 512 threads: the cfg5 class): every lane keeps its share of its row of W
+// -- up to eight 4-element chunks, chunk c = tl + tpr * i -- in REGISTERS next to the shared-memory slab (which stays the
+// master copy for W[row, j] reads and the final store).  The per-atom dot product then reads only the column of A from
+// shared memory, 16 bytes per load and the same address for every row of a warp (broadcast): 8 LDS.128 + 32 FFMA per lane
+// instead of 64 scalar LDS + 32 FFMA (ncu of the shared-memory form: issue-active 45 % on the 16 SMs, ~600 warp-instructions
+// per atom).  The one entry that changes per atom is written into the owner lane's register through a uniform switch.
+template <typename T, bool REGW>
+__global__ void __launch_bounds__(REGW ? 512 : 1024, 1) bcd_kernel(const T* __restrict__ Win, const T* __restrict__ A, const T* __restrict__ B,
                            T* __restrict__ Wout, int d, int k, int rpc, int ks, int tpr, int use_mbar) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -72,8 +89,13 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
   double* cs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(slots + 2 * BCD_MAX_CLUSTER) + 7u) & ~(uintptr_t)7u) + 2;
   const int tid = threadIdx.x, nthr = blockDim.x;
   if (use_mbar && tid == 0) {                              // two mbarriers, one per atom parity (see the push below)
-    mbar_init(mbar, (uint32_t)csize);
-    mbar_init(mbar + 8, (uint32_t)csize);
+    // mode 1: csize release-arrives per phase; mode 2: one local arrive.expect_tx + csize st.async completions per phase
+    mbar_init(mbar, use_mbar == 2 ? 1u : (uint32_t)csize);
+    mbar_init(mbar + 8, use_mbar == 2 ? 1u : (uint32_t)csize);
+    if (use_mbar == 2) {                                   // armed for atoms 0 and 1; re-armed for atom j+2 right after the wait of atom j,
+      mbar_expect_tx(mbar, (uint32_t)(csize * sizeof(T)));        // so an expect_tx always precedes the completions it counts
+      mbar_expect_tx(mbar + 8, (uint32_t)(csize * sizeof(T)));
+    }
   }
   const int row0 = rank * rpc;
   const int nrows = max(0, min(rpc, d - row0));
@@ -116,7 +138,33 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
   // on the quarter-rate conversion pipe: measured 0.81 -> 1.32 ms at d=1024, k=256 -- ncu: XU pipe 46 % -- for no
   // measurable change of the dictionary; profiles/r2_other_kernels_ncu.md.)
   // team dot product of this row with column `a` of A (whatever the shared-memory slab holds at the moment)
+  struct __align__(4 * sizeof(T)) V4 { T x, y, z, w; };
+  constexpr int NCH = REGW ? 8 : 1;
+  V4 wr[NCH];
+  int ltpr = 0;                                              // log2(tpr)
+  while ((1 << ltpr) < tpr) ++ltpr;
+  if (REGW) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = tl + tpr * i;
+      wr[i] = (has_row && 4 * c < k) ? *reinterpret_cast<const V4*>(wrow + 4 * c) : V4{T(0), T(0), T(0), T(0)};
+    }
+  }
   auto team_dot = [&](const T* a) -> double {
+    if (REGW) {
+      T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = tl + tpr * i;
+        if (4 * c < k) {
+          const V4 av = *reinterpret_cast<const V4*>(a + 4 * c);
+          a0 += wr[i].x * av.x; a1 += wr[i].y * av.y; a2 += wr[i].z * av.z; a3 += wr[i].w * av.w;
+        }
+      }
+      double dsum = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+      for (int off = tpr >> 1; off > 0; off >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, off);
+      return dsum;
+    }
     T acc0 = T(0), acc1 = T(0);
     if (has_row) {
       int q = tl;
@@ -163,7 +211,11 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
       T v = (tid < (nthr + 31) / 32) ? warp_part[tid] : T(0);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (tid < csize) {
+      if (use_mbar == 2) {
+        if (tid < csize)
+          st_async_cluster(mapa_u32(smem_u32(slots + par * BCD_MAX_CLUSTER + rank), (uint32_t)tid), v,
+                           mapa_u32(mbar + 8u * (uint32_t)par, (uint32_t)tid));
+      } else if (tid < csize) {
         if (use_mbar) {
           // slot (par, rank) of peer `tid`, then a release-arrive on that peer's mbarrier of this parity (csize arrivals per
           // atom).  Slot and mbarrier are reused at atom j+2: this CTA gets there only after it has seen the peer's arrival
@@ -185,14 +237,34 @@ __global__ void __launch_bounds__(1024, 1) bcd_kernel(const T* __restrict__ Win,
       pdot = team_dot(an);                         // (the team's lanes share a warp: these reads precede the write below)
       cj = cs[j + 1];
     }
-    if (use_mbar) mbar_wait(mbar + 8u * (uint32_t)par, (uint32_t)((j >> 1) & 1));
-    else cluster.barrier_wait();
+    if (use_mbar) {
+      mbar_wait(mbar + 8u * (uint32_t)par, (uint32_t)((j >> 1) & 1));
+      if (use_mbar == 2 && tid == 0 && j + 2 < k) mbar_expect_tx(mbar + 8u * (uint32_t)par, (uint32_t)(csize * sizeof(T)));
+    } else {
+      cluster.barrier_wait();
+    }
     T tot = T(0);
     for (int r = 0; r < csize; ++r) tot += slots[par * BCD_MAX_CLUSTER + r];
     const T nrm = sqrt(tot);
     const T sc = T(1) / (nrm > T(1) ? nrm : T(1));
     const T wfin = sc * wnew;
     if (has_row && tl == 0) Ws[(size_t)rl * ks + j] = wfin;
+    if (REGW) {
+      const int cj4 = j >> 2;                                // chunk of entry j; owner lane cj4 % tpr, its chunk slot cj4 / tpr
+      if (has_row && tl == (cj4 & (tpr - 1))) {
+        switch (((cj4 >> ltpr) << 2) | (j & 3)) {           // (uniform)
+#define ONMF_BCD_SET(I) \
+          case 4 * I: wr[I < NCH ? I : 0].x = wfin; break;     \
+          case 4 * I + 1: wr[I < NCH ? I : 0].y = wfin; break; \
+          case 4 * I + 2: wr[I < NCH ? I : 0].z = wfin; break; \
+          case 4 * I + 3: wr[I < NCH ? I : 0].w = wfin; break;
+          ONMF_BCD_SET(0) ONMF_BCD_SET(1) ONMF_BCD_SET(2) ONMF_BCD_SET(3)
+          ONMF_BCD_SET(4) ONMF_BCD_SET(5) ONMF_BCD_SET(6) ONMF_BCD_SET(7)
+#undef ONMF_BCD_SET
+          default: break;
+        }
+      }
+    }
     if (j + 1 < k) dot = pdot + (has_row ? ((double)wfin - (double)wold) * (double)an[j] : 0.0);
     __syncwarp();
   }
@@ -450,7 +522,9 @@ static int update_dict_t(const T* Win, const T* A, const T* B, int d, int k, T* 
   }
   int threads = round_up(rpc * tpr, 32);
   if (threads > 1024) threads = 1024;
-  auto kern = bcd_kernel<T>;
+  static const int regw_on = [] { const char* e = getenv("ONMF_BCD_REGW"); return (e && atoi(e) == 0) ? 0 : 1; }();   // (A/B runs)
+  const bool regw = regw_on && sizeof(T) == 4 && k % 4 == 0 && tpr >= 4 && k <= 32 * tpr && threads <= 512;
+  auto kern = regw ? bcd_kernel<T, sizeof(T) == 4> : bcd_kernel<T, false>;
   ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (cs > 8) ONMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
@@ -465,7 +539,7 @@ static int update_dict_t(const T* Win, const T* A, const T* B, int d, int k, T* 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  static const int use_mbar = [] { const char* e = getenv("ONMF_BCD_MBAR"); return (e && atoi(e) == 0) ? 0 : 1; }();   // (A/B runs)
+  static const int use_mbar = [] { const char* e = getenv("ONMF_BCD_MBAR"); return e ? atoi(e) : 2; }();   // (A/B runs: 0 barrier.cluster, 1 release-arrive, 2 st.async [default])
   ONMF_CUDA(cudaLaunchKernelEx(&cfg, kern, Win, A, B, Wout, d, k, rpc, ks, tpr, use_mbar));
   ++g_launches;
   return ONMF_OK;
