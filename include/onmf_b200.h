@@ -62,7 +62,9 @@ long long onmf_launch_count(void);           /* kernels launched so far by the c
 
 /* img: (H x Wd x C) row-major (C=1 gray / Ising lattice, C=3 colour); coords: n pairs (row, col) of
  * int32 top-left corners; out Xt (n x ld), Xt[j, (r*p + c)*C + ch] = img[a_j + r, b_j + c, ch]
- * -- the HWC feature order of the reference's reshape(k**2, 3) + mode-2 joint unfolding. */
+ * -- the HWC feature order of the reference's reshape(k**2, 3) + mode-2 joint unfolding.  ld >= p*p*C is the row pitch of Xt in
+ * elements (nothing is written beyond a patch's p*p*C features).  16-byte stores whenever p*p*C and ld are multiples of 16 bytes
+ * and Xt is 16-byte aligned, scalar otherwise; same bytes either way. */
 int onmf_gather_patches(int dtype, const void* img, int H, int Wd, int C, const int32_t* coords,
                         int64_t n, int p, void* Xt, int64_t ld, void* stream);
 
@@ -234,7 +236,10 @@ int onmf_surrogate_fused_tc(const void* Ht, int src_kind, const void* pool, int6
  * replaces: update_dict  src/ontf.py:91-115 == src/onmf.py:92-116
  *   for j in 0..k-1:  W[:,j] -= (W A[:,j] - B[j,:]^T) / (A[j,j] + 1);  W[:,j] = max(W[:,j], 0);
  *                     W[:,j] /= max(1, ||W[:,j]||_2)
- * W_in and W_out (d x k) may alias.
+ * W_in and W_out (d x k) may alias.  Three kernels, chosen by shape: one CTA (d <= 1024 and W, A within its shared memory),
+ * one 16-CTA thread-block cluster (d*k up to ~0.9 M fp32 entries), a cooperative grid beyond that (onmf_update_dict_ws with a
+ * workspace).  Each is deterministic and gives bit-identical results on every GPU of a data-parallel run; the three differ from
+ * one another in summation order (last bits).
  * ------------------------------------------------------------------------------------------- */
 int onmf_update_dict(int dtype, const void* W_in, const void* A, const void* B, int d, int k,
                      void* W_out, void* stream);
@@ -264,7 +269,9 @@ int onmf_pgd_sweep_rows(int dtype, const void* G, const void* Ct, int64_t n, int
  * image_reconstruction.py:375-392 (one update_code_within_radius call + k*k python paints per patch)
  * ------------------------------------------------------------------------------------------- */
 /* the complete projected-gradient coder per sample (outer loop + per-sample stopping test in-kernel), i.e. what the
- * reference computes when it calls update_code_within_radius on ONE patch at a time; Ht (n x k) holds H0 on entry */
+ * reference computes when it calls update_code_within_radius on ONE patch at a time; Ht (n x k) holds H0 on entry.
+ * One warp per sample; for k <= 32 and n >= 16 x SMs one thread per sample (same iteration and stopping test, dot products summed
+ * in index order instead of butterfly order: results agree to rounding, not bit for bit). */
 int onmf_pgd_code_columns(int dtype, const void* G, const void* Ct, int64_t n, int k, double alpha, int sub_iter,
                           double stopping_diff, void* Ht, void* stream);
 /* overlap-averaged canvas (H x W x C) from the reconstructions R ((ny*nx) x ldr) of the p x p patches whose top-left
