@@ -45,13 +45,20 @@ def extract_patches_2d(img, patch_size, precision=None, device=False):
     corners (i, j), i in 0..H-k, j in 0..W-k (the last offset INCLUDED, unlike the random sampler), row-major.
     Returns X (k*k*C, N) numpy float64, or the sample-major device tensor (N x k*k*C) with device=True."""
     A = np.asarray(img)
-    k = int(patch_size)
-    ny, nx = A.shape[0] - k + 1, A.shape[1] - k + 1
-    if ny <= 0 or nx <= 0:
-        raise ValueError("patch_size %d larger than the image %s" % (k, A.shape[:2]))
-    gy, gx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
-    coords = np.stack([gy.reshape(-1), gx.reshape(-1)], 1).astype(np.int32)
-    return gather_patches(A, coords, k, precision, device)
+    return gather_patches(A, all_patch_coords(A.shape, patch_size), int(patch_size), precision, device)
+
+
+def all_patch_coords(shape, patch_size, stride=1, include_last=True):
+    """Top-left corners of a patch grid, row-major, as an (N x 2) int32 array.  include_last=True: every offset 0..H-k
+    (sklearn's extract_patches_2d order); False: `range(0, H - k, stride)` -- the grid of the drivers' reconstruction loop
+    (image_reconstruction.py:375-376), which leaves the last offset out."""
+    k, s = int(patch_size), int(stride)
+    if k > shape[0] or k > shape[1]:
+        raise ValueError("patch_size %d larger than the image %s" % (k, tuple(shape[:2])))
+    ys = np.arange(0, shape[0] - k + (1 if include_last else 0), s)
+    xs = np.arange(0, shape[1] - k + (1 if include_last else 0), s)
+    gy, gx = np.meshgrid(ys, xs, indexing="ij")
+    return np.stack([gy.reshape(-1), gx.reshape(-1)], 1).astype(np.int32)
 
 
 def extract_random_patches(img, patch_size, num_patches, precision=None):
